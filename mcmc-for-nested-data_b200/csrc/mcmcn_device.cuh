@@ -1,0 +1,774 @@
+// mcmcn_device.cuh -- device code of the B200-native MCMC step path (sm_100a).
+//
+// What the reference does per iteration (posteriorSampling.py:594-613): for each
+// parameter name, propose for every group, call the user objective once over
+// all observations, sum per group, run the Metropolis decision tree per group,
+// tune, then Gibbs-update that name's hyper-parameters.  Here thousands of
+// chains advance together:
+//
+//   * lanes = chains.  A warp holds 32*C chains of ONE group; the group's
+//     observation block is staged once into shared memory by a TMA bulk copy
+//     and every shared-memory read in the hot loop is a warp-uniform broadcast.
+//     Per-group sums are per-thread (no shuffles), FP32 per observation, folded
+//     into FP64 every 4 observations (reference: sequential fp64 sum, :631-633).
+//   * chain state lives in HBM/L2 as [P][G][S] fp64 arrays (chain fastest) and is
+//     touched once per (chain, group, sweep); the hot loop runs from registers.
+//   * a sweep over name p needs the hyper-parameters of p from the previous
+//     iteration only, so all P sweeps of a group run back to back in one kernel
+//     and the P Gibbs updates run in one small kernel per iteration.
+//
+// This header is also the source NVRTC compiles for user objectives, so it
+// includes nothing but mcmcn.h.
+#pragma once
+
+#include "mcmcn.h"
+
+namespace mcmcn {
+
+#define MCMCN_LOG_SQRT_2PI 0.91893853320467274178  /* numpy.log(numpy.sqrt(2*numpy.pi)) */
+
+// ---------------------------------------------------------------- small PTX helpers
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned mb, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mb, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned mb) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(mb) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mb, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MCMCN_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MCMCN_DONE;\n"
+        "bra MCMCN_WAIT;\n"
+        "MCMCN_DONE:\n"
+        "}\n" ::"r"(mb), "r"(parity) : "memory");
+}
+
+// ---------------------------------------------------------------- Philox4x32-10
+// Counter-based RNG: key = (global chain id, seed), counter = (iteration lo,
+// iteration hi | stream kind, name*G+group, attempt).  Independent of launch
+// geometry and GPU count.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+#define MCMCN_STREAM_SWEEP 0u
+#define MCMCN_STREAM_HYPER 1u
+#define MCMCN_STREAM_GAMMA 2u
+
+__device__ __forceinline__ uint4 philox_draw(long long chain_id, unsigned long long seed, long long iter,
+                                             unsigned kind, unsigned index, unsigned attempt) {
+    const uint4 ctr = make_uint4((unsigned)iter, ((unsigned)(iter >> 32) & 0x00FFFFFFu) | (kind << 24), index, attempt);
+    const uint2 key = make_uint2((unsigned)chain_id ^ (unsigned)(seed >> 32) * 0x9E3779B1u, (unsigned)seed ^ (unsigned)(chain_id >> 32));
+    return philox4x32_10(ctr, key);
+}
+// standard normal from two 32-bit words (Box-Muller, fp32 resolution; symmetric about 0)
+__device__ __forceinline__ double normal_from(unsigned a, unsigned b) {
+    const float u1 = (float)((a >> 8) + 1u) * 5.9604644775390625e-8f;   // (0, 1]
+    const float u2 = (float)(b >> 8) * 5.9604644775390625e-8f;          // [0, 1)
+    const float r = sqrtf(-2.0f * logf(u1));
+    float s, c;
+    sincospif(2.0f * u2, &s, &c);
+    return (double)(r * c);
+}
+// uniform in [0,1) with 53 random bits, numpy's recipe (legacy random_sample)
+__device__ __forceinline__ double uniform_from(unsigned a, unsigned b) {
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+// ---------------------------------------------------------------- priors (fp64)
+// scipy.stats.norm(loc, scale).logpdf(x): y=(x-loc)/scale; -y**2/2 - log(sqrt(2pi)) - log(scale)
+__device__ __forceinline__ double norm_logpdf(double x, double loc, double scale, double log_scale) {
+    const double y = __ddiv_rn(__dsub_rn(x, loc), scale);
+    const double r = __dsub_rn(__dsub_rn(-0.5 * __dmul_rn(y, y), MCMCN_LOG_SQRT_2PI), log_scale);
+    return (!(scale > 0.0) || y != y) ? __longlong_as_double(0x7ff8000000000000LL) : r;
+}
+__device__ __forceinline__ double prior_logpdf(const mcmcn_prior& pr, double x) {
+    const double ninf = __longlong_as_double(0xfff0000000000000LL);
+    const double nan_ = __longlong_as_double(0x7ff8000000000000LL);
+    if (pr.family == MCMCN_PRIOR_NORM) return norm_logpdf(x, pr.loc, pr.scale, pr.log_scale);
+    const double y = __ddiv_rn(__dsub_rn(x, pr.loc), pr.scale);
+    if (!(pr.scale > 0.0) || y != y) return nan_;
+    double r;
+    switch (pr.family) {
+        case MCMCN_PRIOR_GAMMA: {  // xlogy(a-1, y) - y - gammaln(a)
+            if (y < 0.0) return ninf;
+            const double am1 = pr.a - 1.0;
+            const double xl = (am1 == 0.0) ? 0.0 : am1 * log(y);
+            r = __dsub_rn(__dsub_rn(xl, y), pr.c0);
+            break;
+        }
+        case MCMCN_PRIOR_UNIFORM:
+            if (y < 0.0 || y > 1.0) return ninf;
+            r = 0.0;
+            break;
+        case MCMCN_PRIOR_EXPON:
+            if (y < 0.0) return ninf;
+            r = -y;
+            break;
+        case MCMCN_PRIOR_HALFNORM:  // 0.5*log(2/pi) - y*y/2
+            if (y < 0.0) return ninf;
+            r = __dsub_rn(-0.22579135264472741, 0.5 * __dmul_rn(y, y));
+            break;
+        default:
+            return nan_;
+    }
+    return __dsub_rn(r, pr.log_scale);
+}
+
+// ---------------------------------------------------------------- objective policies
+// A policy restates one reference-style objective as a device function over a
+// group's packed block in shared memory.  `accumulate` adds the block's
+// contribution for C chains at once (th[c][p] = parameter p of chain slot c),
+// `finish` turns the accumulator into the group log-likelihood, `pointwise`
+// gives one observation's log-likelihood (saveLogLikelihood path).
+
+template <typename T> struct Vec4 {};
+template <> struct Vec4<float> {
+    __device__ static __forceinline__ void load(const float* p, float (&v)[4]) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+};
+template <> struct Vec4<double> {
+    __device__ static __forceinline__ void load(const double* p, double (&v)[4]) {
+        const double2 a = *reinterpret_cast<const double2*>(p);
+        const double2 b = *reinterpret_cast<const double2*>(p + 2);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+};
+__device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
+
+// Linear regression with K coefficients and a noise sd (example/regression.py:53-67):
+//   ll_i = norm(loc=y_i, scale=sigma).logpdf(x_i . b)
+// Block: ceil(R/4) quads of [4 obs][KP] x followed by [4] e.
+// FP32 conditioning: the residual x_i.b - y_i cancels catastrophically when |y| >> |residual|
+// (the reference's own example has |y| ~ 300 against residuals ~ 1).  The host therefore
+// centres every group on a reference point bbar_g (its least-squares fit, FP64, in
+// obj_const[g*K + k]) and stores e_i = y_i - x_i.bbar_g instead of y_i; the kernel evaluates
+// the identical residual as x_i.(b - bbar_g) - e_i with (b - bbar_g) formed in FP64.
+template <int K_>
+struct LinReg {
+    static constexpr int K = K_;
+    static constexpr int P = K_ + 1;
+    static constexpr int KP = (K_ + 3) & ~3;
+    static constexpr int UNIT = 4 * KP + 4;      // elements per quad
+    static constexpr int HDR = 0;
+    static constexpr int OBS_PER_UNIT = 4;
+
+    // parameter p of group g as the kernel's working value
+    template <typename T>
+    __device__ static __forceinline__ T local(int p, double v, const double* cst, int g) {
+        return (T)(p < K ? __dsub_rn(v, cst[(size_t)g * K + p]) : v);
+    }
+
+    template <int C, typename T>
+    __device__ static __forceinline__ void accumulate(const T* __restrict__ blk, int nobs, const double*,
+                                                      const T (&th)[C][P], double (&acc)[C]) {
+        const int nq = nobs >> 2;
+        for (int q = 0; q < nq; ++q) {
+            const T* xq = blk + (size_t)q * UNIT;
+            T y4[4];
+            Vec4<T>::load(xq + 4 * KP, y4);
+            T s[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) s[c] = (T)0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                T x[KP];
+#pragma unroll
+                for (int k4 = 0; k4 < KP; k4 += 4) {
+                    T v[4];
+                    Vec4<T>::load(xq + j * KP + k4, v);
+                    x[k4] = v[0]; x[k4 + 1] = v[1]; x[k4 + 2] = v[2]; x[k4 + 3] = v[3];
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    T r = -y4[j];
+#pragma unroll
+                    for (int k = 0; k < K; ++k) r = fma_t(x[k], th[c][k], r);
+                    s[c] = fma_t(r, r, s[c]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] += (double)s[c];
+        }
+        const int rem = nobs & 3;
+        if (rem) {
+            const T* xq = blk + (size_t)nq * UNIT;
+            T s[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) s[c] = (T)0;
+            for (int j = 0; j < rem; ++j) {
+                const T y = xq[4 * KP + j];
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    T r = -y;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) r = fma_t(xq[j * KP + k], th[c][k], r);
+                    s[c] = fma_t(r, r, s[c]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] += (double)s[c];
+        }
+    }
+    template <typename T>
+    __device__ static __forceinline__ double finish(double acc, int R, const double*, const T (&th)[P]) {
+        const double sg = (double)th[K];
+        if (!(sg > 0.0)) return __longlong_as_double(0x7ff8000000000000LL);   // scipy: scale <= 0 -> nan
+        const double inv = 1.0 / sg;
+        return -0.5 * acc * inv * inv - (double)R * (log(sg) + MCMCN_LOG_SQRT_2PI);
+    }
+    template <typename T>
+    __device__ static __forceinline__ double pointwise(const T* __restrict__ blk, int i, const double*, const T (&th)[P]) {
+        const T* xq = blk + (size_t)(i >> 2) * UNIT;
+        const int j = i & 3;
+        T r = -xq[4 * KP + j];
+#pragma unroll
+        for (int k = 0; k < K; ++k) r = fma_t(xq[j * KP + k], th[k], r);
+        const double sg = (double)th[K];
+        if (!(sg > 0.0)) return __longlong_as_double(0x7ff8000000000000LL);
+        const double z = (double)r / sg;
+        return -0.5 * z * z - MCMCN_LOG_SQRT_2PI - log(sg);
+    }
+};
+
+// Bernoulli-logit: ll_i = y_i*eta_i - log(1+exp(eta_i)), eta_i = a + b*x_i.
+// Block: ceil(R/4) quads of [4] x followed by [4] y.
+__device__ __forceinline__ float softplus_t(float eta) {
+    return fmaxf(eta, 0.0f) + __logf(1.0f + __expf(-fabsf(eta)));     // 2 MUFU per evaluation
+}
+__device__ __forceinline__ double softplus_t(double eta) {
+    return fmax(eta, 0.0) + log1p(exp(-fabs(eta)));
+}
+struct Logit {
+    static constexpr int P = 2;
+    static constexpr int UNIT = 8;
+    static constexpr int HDR = 0;
+    static constexpr int OBS_PER_UNIT = 4;
+
+    template <typename T>
+    __device__ static __forceinline__ T local(int, double v, const double*, int) { return (T)v; }
+
+    template <int C, typename T>
+    __device__ static __forceinline__ void accumulate(const T* __restrict__ blk, int nobs, const double*,
+                                                      const T (&th)[C][P], double (&acc)[C]) {
+        const int nq = nobs >> 2;
+        for (int q = 0; q < nq; ++q) {
+            T x4[4], y4[4];
+            Vec4<T>::load(blk + (size_t)q * UNIT, x4);
+            Vec4<T>::load(blk + (size_t)q * UNIT + 4, y4);
+            T s[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) s[c] = (T)0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const T eta = fma_t(th[c][1], x4[j], th[c][0]);
+                    s[c] += fma_t(y4[j], eta, -softplus_t(eta));
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] += (double)s[c];
+        }
+        const int rem = nobs & 3;
+        const T* xq = blk + (size_t)nq * UNIT;
+        for (int j = 0; j < rem; ++j) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const T eta = fma_t(th[c][1], xq[j], th[c][0]);
+                acc[c] += (double)fma_t(xq[4 + j], eta, -softplus_t(eta));
+            }
+        }
+    }
+    template <typename T>
+    __device__ static __forceinline__ double finish(double acc, int, const double*, const T (&)[P]) { return acc; }
+    template <typename T>
+    __device__ static __forceinline__ double pointwise(const T* __restrict__ blk, int i, const double*, const T (&th)[P]) {
+        const T* xq = blk + (size_t)(i >> 2) * UNIT;
+        const T eta = fma_t(th[1], xq[i & 3], th[0]);
+        return (double)fma_t(xq[4 + (i & 3)], eta, -softplus_t(eta));
+    }
+};
+
+// Gaussian "distribution" objective (example/distribution.py:18-24):
+//   ll_i = sum_j norm(mu_j[g(i)], sd_j).logpdf(theta_j)
+// The example has no per-observation data (every row of a group is identical), but under
+// complete pooling the single stepped group mixes rows of different original groups, so the
+// packed record of observation i carries its own mu_j[g(i)].
+// Block: ceil(R/4) quads of [4 obs][PP] mu, PP = P rounded up to 4.  obj_const = sd[P] then log(sd)[P].
+template <int P_>
+struct GaussDist {
+    static constexpr int P = P_;
+    static constexpr int PP = (P_ + 3) & ~3;
+    static constexpr int UNIT = 4 * PP;
+    static constexpr int HDR = 0;
+    static constexpr int OBS_PER_UNIT = 4;
+
+    template <typename T>
+    __device__ static __forceinline__ T local(int, double v, const double*, int) { return (T)v; }
+
+    template <typename T>
+    __device__ static __forceinline__ T row(const T* __restrict__ rec, const double* cst, const T (&th)[P]) {
+        T v = (T)0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            const T y = (th[j] - rec[j]) / (T)cst[j];
+            v = v + ((-(y * y) / (T)2 - (T)MCMCN_LOG_SQRT_2PI) - (T)cst[P + j]);
+        }
+        return v;
+    }
+    template <int C, typename T>
+    __device__ static __forceinline__ void accumulate(const T* __restrict__ blk, int nobs, const double* cst,
+                                                      const T (&th)[C][P], double (&acc)[C]) {
+        for (int i = 0; i < nobs; ++i) {   // one evaluation per observation, summed in order (:631-633)
+            const T* rec = blk + (size_t)(i >> 2) * UNIT + (i & 3) * PP;
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] = __dadd_rn(acc[c], (double)row<T>(rec, cst, th[c]));
+        }
+    }
+    template <typename T>
+    __device__ static __forceinline__ double finish(double acc, int, const double*, const T (&)[P]) { return acc; }
+    template <typename T>
+    __device__ static __forceinline__ double pointwise(const T* __restrict__ blk, int i, const double* cst, const T (&th)[P]) {
+        return (double)row<T>(blk + (size_t)(i >> 2) * UNIT + (i & 3) * PP, cst, th);
+    }
+};
+
+// ---------------------------------------------------------------- kernel arguments
+struct SweepArgs {
+    // model
+    const void* data;
+    const long long* group_off;
+    const int* group_nobs;
+    const int* task_group0;
+    const double* obj_const;
+    int P, G;
+    int partial;
+    int tile_cap_elems;
+    mcmcn_prior prior[MCMCN_MAX_PARAMS];
+    // state
+    int n_chains, S;
+    long long chain_id0;
+    double* theta;
+    double* scale;
+    unsigned* counts;
+    double* ll;
+    double* lprior;
+    const double* hyper;
+    // iteration
+    long long iter;
+    unsigned long long seed;
+    int tune, count, use_override;
+    const double* tape_z;
+    const double* tape_u;
+    const unsigned char* tape_acc;
+    double* tr_ll;
+    double* tr_lp;
+    double* tr_diff;
+    unsigned char* tr_acc;
+    // eval-only mode
+    const double* pooled_theta;   // [P][S] or NULL
+    double* out_ll;               // [G][S]
+};
+
+// Stage `elems` elements starting at `src` into the tile and wait for them.
+// All threads of the CTA call this; thread 0 issues the TMA bulk copy.
+template <typename T>
+__device__ __forceinline__ void stage_tile(T* tile, const T* src, long long elems, unsigned mb, unsigned& parity,
+                                           bool need_sync) {
+    if (need_sync) __syncthreads();          // previous readers of the tile are done
+    if (threadIdx.x == 0) {
+        const unsigned bytes = (unsigned)(elems * (long long)sizeof(T));
+        mbar_expect_tx(mb, bytes);
+        tma_bulk_g2s(smem_u32(tile), src, bytes, mb);
+    }
+    mbar_wait(mb, parity);
+    parity ^= 1u;
+}
+
+// Group log-likelihood for C chains; the group's block is either resident in
+// the tile (blk != NULL) or streamed through it in chunks.
+template <class Obj, int C, typename T>
+__device__ __forceinline__ void group_loglik(const SweepArgs& a, const T* blk, T* tile, int g, int R, unsigned mb,
+                                             unsigned& parity, const T (&th)[C][Obj::P], double (&out)[C]) {
+    double acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.0;
+    if (blk != nullptr) {
+        Obj::template accumulate<C, T>(blk + Obj::HDR, R, a.obj_const, th, acc);
+    } else {
+        // streaming: header stays out of the tile (objectives with a header always fit)
+        const T* src = reinterpret_cast<const T*>(a.data) + a.group_off[g] + Obj::HDR;
+        const int unit = Obj::UNIT > 0 ? Obj::UNIT : 1;
+        const int chunk_obs = (a.tile_cap_elems / unit) * Obj::OBS_PER_UNIT;
+        for (int o = 0; o < R; o += chunk_obs) {
+            const int n = min(chunk_obs, R - o);
+            const long long elems = (long long)((n + Obj::OBS_PER_UNIT - 1) / Obj::OBS_PER_UNIT) * Obj::UNIT;
+            stage_tile<T>(tile, src + (long long)(o / Obj::OBS_PER_UNIT) * Obj::UNIT, elems, mb, parity, true);
+            Obj::template accumulate<C, T>(tile, n, a.obj_const, th, acc);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) out[c] = Obj::template finish<T>(acc[c], R, a.obj_const, th[c]);
+}
+
+// ---------------------------------------------------------------- the step kernel
+// grid = (tasks, chain blocks); block = NW warps; one warp = 32*C chains of one group at a time.
+// MINB = minimum resident CTAs per SM the register allocation must allow (2 -> at most 128 registers).
+template <class Obj, int C, typename T, int MINB>
+__global__ void __launch_bounds__(256, MINB) sweep_kernel(const SweepArgs a) {
+    constexpr int P = Obj::P;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* tile = reinterpret_cast<T*>(smem_raw);
+    __shared__ unsigned long long mbar_storage;
+    const unsigned mb = smem_u32(&mbar_storage);
+
+    const int task = blockIdx.x;
+    const int g0 = a.task_group0[task], g1 = a.task_group0[task + 1];
+    const long long e0 = a.group_off[g0], e1 = a.group_off[g1];
+    const bool fits = (e1 - e0) <= (long long)a.tile_cap_elems;
+    if (threadIdx.x == 0) mbar_init(mb, 1);
+    __syncthreads();
+    unsigned parity = 0;
+    if (fits) stage_tile<T>(tile, reinterpret_cast<const T*>(a.data) + e0, e1 - e0, mb, parity, false);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int cbase = (blockIdx.y * nw + warp) * (32 * C) + lane;
+    const size_t S = (size_t)a.S;
+    const double nan_ = __longlong_as_double(0x7ff8000000000000LL);
+
+    for (int g = g0; g < g1; ++g) {
+        const int R = a.group_nobs[g];
+        const T* blk = fits ? tile + (a.group_off[g] - e0) : nullptr;
+
+        T th[C][P];
+        double llcur[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int ch = cbase + 32 * c;
+            const bool on = ch < a.n_chains;
+#pragma unroll
+            for (int p = 0; p < P; ++p)
+                th[c][p] = on ? Obj::template local<T>(p, a.theta[((size_t)p * a.G + g) * S + ch], a.obj_const, g) : (T)1;
+            llcur[c] = on ? a.ll[(size_t)g * S + ch] : 0.0;
+        }
+
+#pragma unroll 1
+        for (int p = 0; p < P; ++p) {
+            const size_t row = ((size_t)p * a.G + g) * S;
+            double cur[C], prop[C], sc[C], uu[C];
+            T old[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int ch = cbase + 32 * c;
+                const bool on = ch < a.n_chains;
+                cur[c] = on ? a.theta[row + ch] : 1.0;
+                sc[c] = on ? a.scale[row + ch] : 1.0;
+                double z;
+                if (a.tape_z != nullptr) {
+                    z = on ? a.tape_z[row + ch] : 0.0;
+                    uu[c] = on ? a.tape_u[row + ch] : 0.5;
+                } else {
+                    const uint4 rnd = philox_draw(a.chain_id0 + ch, a.seed, a.iter, MCMCN_STREAM_SWEEP,
+                                                  (unsigned)(p * a.G + g), 0u);
+                    z = normal_from(rnd.x, rnd.y);
+                    uu[c] = uniform_from(rnd.z, rnd.w);
+                }
+                prop[c] = __dadd_rn(cur[c], __dmul_rn(sc[c], z));      // numpy.random.normal(value, sd), :304-306
+                const T pt = Obj::template local<T>(p, prop[c], a.obj_const, g);
+#pragma unroll
+                for (int k = 0; k < P; ++k) {
+                    if (k == p) { old[c] = th[c][k]; th[c][k] = pt; }
+                }
+            }
+
+            double llp[C];
+            group_loglik<Obj, C, T>(a, blk, tile, g, R, mb, parity, th, llp);
+
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int ch = cbase + 32 * c;
+                const bool on = ch < a.n_chains;
+                double lp_prop, lp_cur;
+                if (a.partial) {
+                    const double mu = on ? a.hyper[((size_t)0 * P + p) * S + ch] : 0.0;
+                    const double sd = on ? a.hyper[((size_t)2 * P + p) * S + ch] : 1.0;
+                    const double lsd = on ? a.hyper[((size_t)3 * P + p) * S + ch] : 0.0;
+                    lp_prop = norm_logpdf(prop[c], mu, sd, lsd);
+                    lp_cur = a.use_override ? (on ? a.lprior[row + ch] : 0.0) : norm_logpdf(cur[c], mu, sd, lsd);
+                } else {
+                    lp_prop = prior_logpdf(a.prior[p], prop[c]);
+                    lp_cur = on ? a.lprior[row + ch] : 0.0;
+                }
+                // Parameter.step decision tree, :334-367
+                const double post_prop = lp_prop + llp[c];
+                const double post_cur = lp_cur + llcur[c];
+                const double diff = post_prop - post_cur;
+                bool acc_own;
+                if (!isfinite(post_cur) && isfinite(post_prop)) acc_own = true;
+                else if (!isfinite(llp[c])) acc_own = false;
+                else if (!isfinite(diff)) acc_own = false;
+                else acc_own = log(uu[c]) < diff;
+                bool accept = acc_own;
+                if (on) {
+                    if (a.tr_ll != nullptr) {
+                        a.tr_ll[row + ch] = llp[c];
+                        a.tr_lp[row + ch] = lp_prop;
+                        a.tr_diff[row + ch] = diff;
+                        a.tr_acc[row + ch] = acc_own ? 1 : 0;
+                    }
+                    if (a.tape_acc != nullptr) accept = a.tape_acc[row + ch] != 0;
+                }
+                accept = accept && on;
+                if (accept) {                                        // :369-378, :608-610
+                    a.theta[row + ch] = prop[c];
+                    llcur[c] = llp[c];
+                    if (!a.partial) a.lprior[row + ch] = lp_prop;
+                }
+#pragma unroll
+                for (int k = 0; k < P; ++k) {
+                    if (k == p && !accept) th[c][k] = old[c];
+                }
+                if (a.count && on) {
+                    unsigned cnt = a.counts[row + ch];
+                    cnt += accept ? 1u : 0x10000u;
+                    if (a.tune) {                                    // Parameter.tune, :385-437
+                        const unsigned na = cnt & 0xFFFFu, nr = cnt >> 16;
+                        if (na + nr) {
+                            const double rate = (double)na / (double)(na + nr);
+                            double f = 1.0;
+                            if (rate < 0.001) f = 0.1;
+                            else if (rate < 0.05) f = 0.5;
+                            else if (rate < 0.2) f = 0.9;
+                            else if (rate > 0.95) f = 10.0;
+                            else if (rate > 0.75) f = 2.0;
+                            else if (rate > 0.5) f = 1.1;
+                            double ns = __dmul_rn(sc[c], f);
+                            if (ns == 0.0) ns = sc[c];
+                            a.scale[row + ch] = ns;
+                            cnt = 0;
+                        }
+                    }
+                    a.counts[row + ch] = cnt;
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int ch = cbase + 32 * c;
+            if (ch < a.n_chains) a.ll[(size_t)g * S + ch] = llcur[c];
+        }
+        (void)nan_;
+    }
+}
+
+// Group log-likelihood of the current (or pooled) parameter values, no proposal.
+template <class Obj, int C, typename T>
+__global__ void __launch_bounds__(256) eval_kernel(const SweepArgs a) {
+    constexpr int P = Obj::P;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* tile = reinterpret_cast<T*>(smem_raw);
+    __shared__ unsigned long long mbar_storage;
+    const unsigned mb = smem_u32(&mbar_storage);
+    const int task = blockIdx.x;
+    const int g0 = a.task_group0[task], g1 = a.task_group0[task + 1];
+    const long long e0 = a.group_off[g0], e1 = a.group_off[g1];
+    const bool fits = (e1 - e0) <= (long long)a.tile_cap_elems;
+    if (threadIdx.x == 0) mbar_init(mb, 1);
+    __syncthreads();
+    unsigned parity = 0;
+    if (fits) stage_tile<T>(tile, reinterpret_cast<const T*>(a.data) + e0, e1 - e0, mb, parity, false);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int cbase = (blockIdx.y * nw + warp) * (32 * C) + lane;
+    const size_t S = (size_t)a.S;
+    for (int g = g0; g < g1; ++g) {
+        const int R = a.group_nobs[g];
+        const T* blk = fits ? tile + (a.group_off[g] - e0) : nullptr;
+        T th[C][P];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int ch = cbase + 32 * c;
+            const bool on = ch < a.n_chains;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                double v = 1.0;
+                if (on) v = a.pooled_theta ? a.pooled_theta[(size_t)p * S + ch] : a.theta[((size_t)p * a.G + g) * S + ch];
+                th[c][p] = Obj::template local<T>(p, v, a.obj_const, g);
+            }
+        }
+        double out[C];
+        group_loglik<Obj, C, T>(a, blk, tile, g, R, mb, parity, th, out);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int ch = cbase + 32 * c;
+            if (ch < a.n_chains) a.out_ll[(size_t)g * S + ch] = out[c];
+        }
+    }
+}
+
+// Pointwise log-likelihood of the current state (saveLogLikelihood, :656-659, :907-909).
+// Not a hot path: reads the blocks straight from global memory.  grid = (G, chain blocks of 128).
+template <class Obj, typename T>
+__global__ void pointwise_kernel(const SweepArgs a, const long long* obs_off, double* out) {
+    constexpr int P = Obj::P;
+    const int g = blockIdx.x;
+    const int ch = blockIdx.y * blockDim.x + threadIdx.x;
+    if (ch >= a.n_chains) return;
+    const size_t S = (size_t)a.S;
+    T th[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) th[p] = Obj::template local<T>(p, a.theta[((size_t)p * a.G + g) * S + ch], a.obj_const, g);
+    const T* blk = reinterpret_cast<const T*>(a.data) + a.group_off[g];
+    const int R = a.group_nobs[g];
+    const long long o0 = obs_off[g];
+    for (int i = 0; i < R; ++i)
+        out[(size_t)(o0 + i) * S + ch] = Obj::template pointwise<T>(blk + Obj::HDR, i, a.obj_const, th);
+}
+
+// ---------------------------------------------------------------- Gibbs hyper update
+// HyperParameter.update (posteriorSampling.py:463-498) + the new prior's sd / log sd
+// (getDistribution :500-502).  One block = 32 chains x NS group slices for one name.
+struct HyperArgs {
+    int P, G, n_chains, S;
+    long long chain_id0;
+    const double* theta;
+    double* hyper;
+    long long iter;
+    unsigned long long seed;
+    const double* tape_zmu;     // [P][S] or NULL
+    const double* tape_qsig;    // [P][S] or NULL
+};
+
+// Gamma(a, 1) by Marsaglia-Tsang on the chain's Philox stream.
+__device__ inline double gamma_draw(double a, long long chain_id, unsigned long long seed, long long iter, unsigned p) {
+    const bool boost = a < 1.0;
+    const double aa = boost ? a + 1.0 : a;
+    const double d = aa - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    double g = d;
+    for (unsigned k = 0; k < 64u; ++k) {
+        const uint4 r = philox_draw(chain_id, seed, iter, MCMCN_STREAM_GAMMA, p, k);
+        const double x = normal_from(r.x, r.y);
+        double v = 1.0 + c * x;
+        if (v <= 0.0) continue;
+        v = v * v * v;
+        const double u = uniform_from(r.z, r.w);
+        if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) { g = d * v; break; }
+    }
+    if (boost) {
+        const uint4 r = philox_draw(chain_id, seed, iter, MCMCN_STREAM_GAMMA, p, 1000u);
+        g *= pow(uniform_from(r.x, r.y) + 1.1102230246251565e-16, 1.0 / a);
+    }
+    return g;
+}
+
+template <int NS>
+__global__ void __launch_bounds__(32 * NS) hyper_kernel(const HyperArgs a) {
+    __shared__ double red[NS][33];
+    __shared__ double mu_s[32];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int ch = blockIdx.x * 32 + tx;
+    const int p = blockIdx.y;
+    const bool on = ch < a.n_chains;
+    const size_t S = (size_t)a.S;
+    const double* th = a.theta + ((size_t)p * a.G) * S + ch;
+    const double n = (double)a.G;
+
+    // pass 1: mean (numpy.mean, :485)
+    double s = 0.0;
+    if (on) for (int g = ty; g < a.G; g += NS) s += th[(size_t)g * S];
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) t += red[k][tx];
+        double mu = 0.0;
+        if (on) {
+            const double muHat = t / n;
+            const double sigma2_old = a.hyper[((size_t)1 * a.P + p) * S + ch];
+            const double sd = sqrt(sigma2_old / n);                               // :486
+            double z;
+            if (a.tape_zmu) z = a.tape_zmu[(size_t)p * S + ch];
+            else {
+                const uint4 r = philox_draw(a.chain_id0 + ch, a.seed, a.iter, MCMCN_STREAM_HYPER, (unsigned)p, 0u);
+                z = normal_from(r.x, r.y);
+            }
+            mu = __dadd_rn(muHat, __dmul_rn(sd, z));                               // :487
+        }
+        mu_s[tx] = mu;
+    }
+    __syncthreads();
+    // pass 2: sum of squares about the NEW mu (:494)
+    const double mu = mu_s[tx];
+    s = 0.0;
+    if (on) for (int g = ty; g < a.G; g += NS) { const double d = th[(size_t)g * S] - mu; s = fma(d, d, s); }
+    __syncthreads();
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && on) {
+        double ss = 0.0;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) ss += red[k][tx];
+        const double hat = ss / (n - 1.0);
+        const double aa = (n - 1.0) / 2.0;
+        double q;                                                                   // unit inverse-gamma draw, :497-498
+        if (a.tape_qsig) q = a.tape_qsig[(size_t)p * S + ch];
+        else q = 1.0 / gamma_draw(aa, a.chain_id0 + ch, a.seed, a.iter, (unsigned)p);
+        const double sigma2 = __dadd_rn(__dmul_rn(q, __dmul_rn(aa, hat)), 0.0);
+        const double sd = sqrt(sigma2);
+        a.hyper[((size_t)0 * a.P + p) * S + ch] = mu;
+        a.hyper[((size_t)1 * a.P + p) * S + ch] = sigma2;
+        a.hyper[((size_t)2 * a.P + p) * S + ch] = sd;
+        a.hyper[((size_t)3 * a.P + p) * S + ch] = log(sd);
+    }
+}
+
+// ---------------------------------------------------------------- retained-sample write-back
+// One row of StepMethod.values (:648-654, :780-787): per name [mu, sigma2 (partial)], theta[0..G-1].
+// store[(row*ncol + col)*S + chain]; a warp writes 32 consecutive chains.
+template <typename TS>
+__global__ void snapshot_kernel(int P, int G, int partial, int n_chains, int S, const double* theta,
+                                const double* hyper, TS* store_row) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    const int per = G + (partial ? 2 : 0);
+    const int col = blockIdx.y;
+    if (ch >= n_chains) return;
+    const int p = col / per, j = col - p * per;
+    double v;
+    if (partial && j < 2) v = hyper[((size_t)j * P + p) * S + ch];
+    else v = theta[((size_t)p * G + (j - (partial ? 2 : 0))) * S + ch];
+    store_row[(size_t)col * S + ch] = (TS)v;
+}
+
+__global__ void pooled_nll_kernel(int G, int S, const double* ll, double* out) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= S) return;
+    double s = 0.0;
+    for (int g = 0; g < G; ++g) s += ll[(size_t)g * S + ch];
+    out[ch] = -s;
+}
+
+}  // namespace mcmcn

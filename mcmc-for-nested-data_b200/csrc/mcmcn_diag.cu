@@ -1,0 +1,174 @@
+// mcmcn_diag.cu -- batched reduction kernels behind sampleDiagnosis.diagnoseSamples
+// (/root/reference/sampleDiagnosis.py:158-255, :419-427, :766-776), all FP64 (1e-10 parity bar).
+//
+// Input layout: x[key][half-chain j][draw i], contiguous in i.  The reference loops
+// keys x m x n^2 in pure Python (:189-208); here every (key, half-chain) or (key, lag)
+// pair is one warp / one thread and every sum is taken in a fixed order, so results do
+// not depend on the launch geometry.
+#include <cuda_runtime.h>
+
+#include <cub/device/device_segmented_sort.cuh>
+
+#include "mcmcn_host.h"
+
+namespace mcmcn {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// One warp per (key, half-chain): mean, then sum of squared deviations (two passes,
+// like numpy.var), variance with ddof=1 (:164-166, :174-176).
+__global__ void moments_kernel(const double* __restrict__ x, long long rows, int n, double* __restrict__ mean,
+                               double* __restrict__ var) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const double* p = x + row * (long long)n;
+    double s = 0.0;
+    for (int i = lane; i < n; i += 32) s += p[i];
+    const double mu = warp_sum(s) / (double)n;
+    double q = 0.0;
+    for (int i = lane; i < n; i += 32) { const double d = p[i] - mu; q = fma(d, d, q); }
+    q = warp_sum(q);
+    if (lane == 0) {
+        mean[row] = mu;
+        var[row] = q / (double)(n - 1);
+    }
+}
+
+// Variogram numerators (:189-194): out[key][t] = sum_j sum_{i=t}^{n-1} (x[j][i]-x[j][i-t])^2.
+// Block = one key x one slab of lags; half-chains are staged through shared memory one at
+// a time and accumulated in half-chain order.  Thread `l` owns lags t0+l and, to balance
+// the triangular work, n-1-(t0+l) (lags are paired from both ends).
+__global__ void variogram_kernel(const double* __restrict__ x, int m, int n, double* __restrict__ out) {
+    extern __shared__ double row[];
+    const long long key = blockIdx.x;
+    const int half = (n + 1) / 2;                       // pairs (t, n-1-t), t < half
+    const int t = blockIdx.y * blockDim.x + threadIdx.x;
+    const int ta = t, tb = n - 1 - t;
+    const bool on = t < half;
+    double sa = 0.0, sb = 0.0;
+    for (int j = 0; j < m; ++j) {
+        const double* p = x + (key * m + j) * (long long)n;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) row[i] = p[i];
+        __syncthreads();
+        if (on) {
+            double a = 0.0;
+            for (int i = ta; i < n; ++i) { const double d = row[i] - row[i - ta]; a = fma(d, d, a); }
+            sa += a;
+            if (tb != ta) {
+                double b = 0.0;
+                for (int i = tb; i < n; ++i) { const double d = row[i] - row[i - tb]; b = fma(d, d, b); }
+                sb += b;
+            }
+        }
+    }
+    if (on) {
+        out[key * n + ta] = sa;
+        if (tb != ta) out[key * n + tb] = sb;
+    }
+}
+
+// Median (numpy.median) and shortest interval of `gap` order statistics (:766-776) of one
+// sorted key per block; ties resolve to the smallest index like numpy.where(tmp == min)[0][0].
+__global__ void median_hdi_kernel(const double* __restrict__ s, long long len, long long gap, double* __restrict__ out) {
+    __shared__ double wbest[32];
+    __shared__ long long ibest[32];
+    const double* p = s + (long long)blockIdx.x * len;
+    double w = __longlong_as_double(0x7ff0000000000000LL);
+    long long idx = 0x7fffffffffffffffLL;
+    for (long long i = threadIdx.x; i < len - gap; i += blockDim.x) {
+        const double d = p[i + gap] - p[i];
+        if (d < w || (d == w && i < idx)) { w = d; idx = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double w2 = __shfl_xor_sync(0xffffffffu, w, o);
+        const long long i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (w2 < w || (w2 == w && i2 < idx)) { w = w2; idx = i2; }
+    }
+    if ((threadIdx.x & 31) == 0) { wbest[threadIdx.x >> 5] = w; ibest[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k)
+            if (wbest[k] < w || (wbest[k] == w && ibest[k] < idx)) { w = wbest[k]; idx = ibest[k]; }
+        double* o = out + (long long)blockIdx.x * 3;
+        o[0] = (len & 1) ? p[len / 2] : (p[len / 2 - 1] + p[len / 2]) / 2.0;
+        o[1] = p[idx];
+        o[2] = p[idx + gap];
+    }
+}
+
+}  // namespace mcmcn
+
+using namespace mcmcn;
+
+extern "C" {
+
+int mcmcn_diag_moments(const double* x, int64_t n_keys, int32_t m, int32_t n, double* out_mean, double* out_var,
+                       void* stream) {
+    if (!x || !out_mean || !out_var || n_keys < 1 || m < 1 || n < 2) { set_error("bad diag_moments args"); return MCMCN_ERR_INVALID; }
+    const long long rows = (long long)n_keys * m;
+    const int wpb = 8;
+    moments_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(x, rows, n, out_mean, out_var);
+    CK(cudaGetLastError());
+    return MCMCN_OK;
+}
+
+int mcmcn_diag_variogram(const double* x, int64_t n_keys, int32_t m, int32_t n, double* out, void* stream) {
+    if (!x || !out || n_keys < 1 || m < 1 || n < 2) { set_error("bad diag_variogram args"); return MCMCN_ERR_INVALID; }
+    const size_t smem = sizeof(double) * (size_t)n;
+    if (smem > 200 * 1024) { set_error("n=%d draws per half-chain exceed the shared-memory row buffer", n); return MCMCN_ERR_UNSUPPORTED; }
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(variogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int half = (n + 1) / 2;
+    const int threads = half < 128 ? ((half + 31) & ~31) : 128;
+    const dim3 grid((unsigned)n_keys, (unsigned)((half + threads - 1) / threads), 1);
+    variogram_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(x, m, n, out);
+    CK(cudaGetLastError());
+    return MCMCN_OK;
+}
+
+int mcmcn_diag_median_hdi(const double* sorted, int64_t n_keys, int64_t len, int64_t gap, double* out, void* stream) {
+    if (!sorted || !out || n_keys < 1 || len < 2 || gap < 1 || gap > len - 1) { set_error("bad diag_median_hdi args"); return MCMCN_ERR_INVALID; }
+    median_hdi_kernel<<<(unsigned)n_keys, 256, 0, (cudaStream_t)stream>>>(sorted, len, gap, out);
+    CK(cudaGetLastError());
+    return MCMCN_OK;
+}
+
+int mcmcn_diag_sort_keys(double* x, int64_t n_keys, int64_t len, void* stream_) {
+    if (!x || n_keys < 1 || len < 1) { set_error("bad diag_sort args"); return MCMCN_ERR_INVALID; }
+    if (n_keys * len > (int64_t)0x7fffffff) { set_error("sort of more than 2^31 items not supported"); return MCMCN_ERR_UNSUPPORTED; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int n_items = (int)(n_keys * len);
+    const int n_seg = (int)n_keys;
+    // segment offsets k*len, generated on the host (n_keys is small next to the data)
+    long long* off_h = new long long[n_seg + 1];
+    for (int k = 0; k <= n_seg; ++k) off_h[k] = (long long)k * len;
+    long long* off_d = nullptr;
+    double* tmp = nullptr;
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    int rc = MCMCN_OK;
+    cudaError_t e = cudaMalloc(&off_d, sizeof(long long) * (n_seg + 1));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(off_d, off_h, sizeof(long long) * (n_seg + 1), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMalloc(&tmp, sizeof(double) * (size_t)n_items);
+    if (e == cudaSuccess)
+        e = cub::DeviceSegmentedSort::SortKeys(nullptr, scratch_bytes, x, tmp, n_items, n_seg, off_d, off_d + 1, stream);
+    if (e == cudaSuccess) e = cudaMalloc(&scratch, scratch_bytes ? scratch_bytes : 16);
+    if (e == cudaSuccess)
+        e = cub::DeviceSegmentedSort::SortKeys(scratch, scratch_bytes, x, tmp, n_items, n_seg, off_d, off_d + 1, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(x, tmp, sizeof(double) * (size_t)n_items, cudaMemcpyDeviceToDevice, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { set_error("diag_sort: %s", cudaGetErrorString(e)); rc = MCMCN_ERR_CUDA; }
+    cudaFree(scratch);
+    cudaFree(tmp);
+    cudaFree(off_d);
+    delete[] off_h;
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,310 @@
+// mcmcn_kernels.cu -- ahead-of-time instantiations of the step path for sm_100a and the
+// C-ABI launchers declared in include/mcmcn.h.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "mcmcn_device.cuh"
+#include "mcmcn_host.h"
+
+namespace mcmcn {
+
+thread_local std::string g_last_error;
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+static const int kTileCapBytes = 64 * 1024;
+
+// ---------------------------------------------------------------- kernel registry
+typedef void (*sweep_fn)(const SweepArgs);
+typedef void (*pointwise_fn)(const SweepArgs, const long long*, double*);
+
+struct KernelSet {
+    int objective, P, K, precision;
+    int c_wide;                 // chains per lane of the wide variant
+    sweep_fn sweep_wide, sweep_wide_b1, sweep_one;
+    sweep_fn eval_wide, eval_one;
+    pointwise_fn pointwise;
+    int elem_bytes;
+};
+
+#define MCMCN_SET(OBJ_ID, OBJ, KK, PREC, T, CW)                                                        \
+    {OBJ_ID, OBJ::P, KK, PREC, CW, sweep_kernel<OBJ, CW, T, 2>, sweep_kernel<OBJ, CW, T, 1>, sweep_kernel<OBJ, 1, T, 1>,                  \
+     eval_kernel<OBJ, CW, T>, eval_kernel<OBJ, 1, T>, pointwise_kernel<OBJ, T>, (int)sizeof(T)}
+
+static const KernelSet kSets[] = {
+    MCMCN_SET(MCMCN_OBJ_LINEAR_REGRESSION, LinReg<1>, 1, 32, float, 4),
+    MCMCN_SET(MCMCN_OBJ_LINEAR_REGRESSION, LinReg<1>, 1, 64, double, 2),
+    MCMCN_SET(MCMCN_OBJ_LINEAR_REGRESSION, LinReg<2>, 2, 32, float, 4),
+    MCMCN_SET(MCMCN_OBJ_LINEAR_REGRESSION, LinReg<2>, 2, 64, double, 2),
+    MCMCN_SET(MCMCN_OBJ_LINEAR_REGRESSION, LinReg<4>, 4, 32, float, 4),
+    MCMCN_SET(MCMCN_OBJ_LINEAR_REGRESSION, LinReg<4>, 4, 64, double, 2),
+    MCMCN_SET(MCMCN_OBJ_LINEAR_REGRESSION, LinReg<8>, 8, 32, float, 4),
+    MCMCN_SET(MCMCN_OBJ_LINEAR_REGRESSION, LinReg<8>, 8, 64, double, 2),
+    MCMCN_SET(MCMCN_OBJ_BERNOULLI_LOGIT, Logit, 0, 32, float, 4),
+    MCMCN_SET(MCMCN_OBJ_BERNOULLI_LOGIT, Logit, 0, 64, double, 2),
+    MCMCN_SET(MCMCN_OBJ_GAUSSIAN_DISTRIBUTION, GaussDist<1>, 0, 32, float, 4),
+    MCMCN_SET(MCMCN_OBJ_GAUSSIAN_DISTRIBUTION, GaussDist<1>, 0, 64, double, 2),
+    MCMCN_SET(MCMCN_OBJ_GAUSSIAN_DISTRIBUTION, GaussDist<2>, 0, 32, float, 4),
+    MCMCN_SET(MCMCN_OBJ_GAUSSIAN_DISTRIBUTION, GaussDist<2>, 0, 64, double, 2),
+    MCMCN_SET(MCMCN_OBJ_GAUSSIAN_DISTRIBUTION, GaussDist<3>, 0, 32, float, 4),
+    MCMCN_SET(MCMCN_OBJ_GAUSSIAN_DISTRIBUTION, GaussDist<3>, 0, 64, double, 2),
+    MCMCN_SET(MCMCN_OBJ_GAUSSIAN_DISTRIBUTION, GaussDist<4>, 0, 32, float, 4),
+    MCMCN_SET(MCMCN_OBJ_GAUSSIAN_DISTRIBUTION, GaussDist<4>, 0, 64, double, 2),
+};
+
+static const KernelSet* find_set(int objective, int P, int K, int precision) {
+    for (const KernelSet& s : kSets)
+        if (s.objective == objective && s.P == P && s.precision == precision &&
+            (objective != MCMCN_OBJ_LINEAR_REGRESSION || s.K == K))
+            return &s;
+    return nullptr;
+}
+
+// ---------------------------------------------------------------- launch geometry
+struct Geometry {
+    bool wide;
+    int C, nw;
+    dim3 grid, block;
+    size_t smem;
+};
+
+static int max_task_elems(const mcmcn_model* m) {
+    long long mx = 0;
+    for (int t = 0; t < m->n_tasks; ++t) {
+        const long long e = m->group_off_host[m->task_group0_host[t + 1]] - m->group_off_host[m->task_group0_host[t]];
+        if (e > mx) mx = e;
+    }
+    return (int)(mx > (1LL << 30) ? (1LL << 30) : mx);
+}
+
+static Geometry geometry(const KernelSet* ks, const mcmcn_model* m, int n_chains) {
+    Geometry g;
+    g.wide = n_chains >= 32 * ks->c_wide;
+    g.C = g.wide ? ks->c_wide : 1;
+    const int per_warp = 32 * g.C;
+    int warps = (n_chains + per_warp - 1) / per_warp;
+    g.nw = warps < 8 ? warps : 8;
+    const int gy = (warps + g.nw - 1) / g.nw;
+    g.grid = dim3((unsigned)m->n_tasks, (unsigned)gy, 1);
+    g.block = dim3(32u * g.nw, 1, 1);
+    long long bytes = (long long)max_task_elems(m) * ks->elem_bytes;
+    if (bytes > kTileCapBytes) bytes = kTileCapBytes;
+    if (bytes < 16) bytes = 16;
+    g.smem = (size_t)((bytes + 127) & ~127LL);
+    return g;
+}
+
+static int fill_args(SweepArgs& a, const KernelSet* ks, const mcmcn_model* m, const mcmcn_state* s) {
+    memset(&a, 0, sizeof(a));
+    a.data = m->data;
+    a.group_off = reinterpret_cast<const long long*>(m->group_off);
+    a.group_nobs = m->group_nobs;
+    a.task_group0 = m->task_group0;
+    a.obj_const = m->obj_const;
+    a.P = m->n_params;
+    a.G = m->n_groups;
+    a.partial = m->pooling == MCMCN_POOL_PARTIAL;
+    a.tile_cap_elems = kTileCapBytes / ks->elem_bytes;
+    memcpy(a.prior, m->prior, sizeof(a.prior));
+    a.n_chains = s->n_chains;
+    a.S = s->stride;
+    a.chain_id0 = s->chain_id0;
+    a.theta = s->theta;
+    a.scale = s->scale;
+    a.counts = s->counts;
+    a.ll = s->ll;
+    a.lprior = s->lprior;
+    a.hyper = s->hyper;
+    return MCMCN_OK;
+}
+
+static int validate(const mcmcn_model* m, const mcmcn_state* s, const KernelSet** ks) {
+    if (!m || !s) { set_error("null model/state"); return MCMCN_ERR_INVALID; }
+    if (m->n_params < 1 || m->n_params > MCMCN_MAX_PARAMS) { set_error("n_params %d out of range", m->n_params); return MCMCN_ERR_INVALID; }
+    if (m->n_groups < 1 || m->n_tasks < 1) { set_error("empty model"); return MCMCN_ERR_INVALID; }
+    if (s->n_chains < 1 || s->stride < s->n_chains || (s->stride & 31)) { set_error("bad chain count/stride %d/%d", s->n_chains, s->stride); return MCMCN_ERR_INVALID; }
+    if (!m->task_group0_host || !m->group_off_host) { set_error("host task tables missing"); return MCMCN_ERR_INVALID; }
+    *ks = find_set(m->objective, m->n_params, m->n_coef, m->precision);
+    if (!*ks) {
+        set_error("objective %d with P=%d K=%d precision=%d is not compiled in", m->objective, m->n_params, m->n_coef, m->precision);
+        return MCMCN_ERR_UNSUPPORTED;
+    }
+    return MCMCN_OK;
+}
+
+static int set_smem_attr(const void* fn, size_t smem) {
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return MCMCN_OK;
+}
+
+}  // namespace mcmcn
+
+using namespace mcmcn;
+
+extern "C" {
+
+int mcmcn_version(void) { return MCMCN_VERSION; }
+const char* mcmcn_last_error(void) { return g_last_error.c_str(); }
+int mcmcn_tile_capacity_bytes(void) { return kTileCapBytes; }
+
+int mcmcn_supported(int objective, int n_params, int n_coef, int precision) {
+    return find_set(objective, n_params, n_coef, precision) ? 1 : 0;
+}
+
+int mcmcn_run(const mcmcn_model* m, const mcmcn_state* s, const mcmcn_run_args* r, void* stream_) {
+    const KernelSet* ks = nullptr;
+    int rc = validate(m, s, &ks);
+    if (rc) return rc;
+    if (!r || r->n_iter < 0 || r->thin < 1 || r->tune_interval < 1) { set_error("bad run args"); return MCMCN_ERR_INVALID; }
+    if ((r->tape_z == nullptr) != (r->tape_u == nullptr)) { set_error("tape_z and tape_u go together"); return MCMCN_ERR_INVALID; }
+    const bool partial = m->pooling == MCMCN_POOL_PARTIAL;
+    if (partial && !s->hyper) { set_error("partial pooling needs state.hyper"); return MCMCN_ERR_INVALID; }
+    if (!partial && !s->lprior) { set_error("fixed priors need state.lprior"); return MCMCN_ERR_INVALID; }
+    if (partial && m->n_groups < 2) { set_error("partial pooling needs at least 2 groups"); return MCMCN_ERR_INVALID; }
+    if (partial && r->tape_z && (!r->tape_zmu || !r->tape_qsig)) { set_error("replay of partial pooling needs tape_zmu/tape_qsig"); return MCMCN_ERR_INVALID; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+
+    SweepArgs a;
+    fill_args(a, ks, m, s);
+    const Geometry g = geometry(ks, m, s->n_chains);
+    // MCMCN_MINB=1 selects the variant compiled without the 128-register cap (tuning knob)
+    const char* minb = getenv("MCMCN_MINB");
+    const sweep_fn fn = g.wide ? ((minb && minb[0] == '1') ? ks->sweep_wide_b1 : ks->sweep_wide) : ks->sweep_one;
+    rc = set_smem_attr((const void*)fn, g.smem);
+    if (rc) return rc;
+
+    const size_t S = (size_t)s->stride;
+    const size_t per_iter = (size_t)m->n_params * m->n_groups * S;
+    const size_t per_iter_h = (size_t)m->n_params * S;
+    const int ncol = m->n_params * (m->n_groups + (partial ? 2 : 0));
+    // counters are only ever read by tune(), which stops at the last multiple of tune_interval below burn
+    long long last_tune = 0;
+    if (r->burn > 0) last_tune = ((long long)(r->burn - 1) / r->tune_interval) * r->tune_interval;
+    int64_t row = r->store_row0;
+
+    for (int it = 0; it < r->n_iter; ++it) {
+        const long long i = r->iter0 + it;
+        a.iter = i;
+        a.seed = r->seed;
+        a.tune = (i != 0 && i < r->burn && (i % r->tune_interval) == 0) ? 1 : 0;
+        a.count = (i <= last_tune) ? 1 : 0;
+        a.use_override = (it == 0 && r->use_lprior_override && partial) ? 1 : 0;
+        a.tape_z = r->tape_z ? r->tape_z + it * per_iter : nullptr;
+        a.tape_u = r->tape_u ? r->tape_u + it * per_iter : nullptr;
+        a.tape_acc = r->tape_accept ? r->tape_accept + it * per_iter : nullptr;
+        a.tr_ll = r->trace_ll ? r->trace_ll + it * per_iter : nullptr;
+        a.tr_lp = r->trace_lp ? r->trace_lp + it * per_iter : nullptr;
+        a.tr_diff = r->trace_diff ? r->trace_diff + it * per_iter : nullptr;
+        a.tr_acc = r->trace_accept ? r->trace_accept + it * per_iter : nullptr;
+        if (a.tr_ll && !(a.tr_lp && a.tr_diff && a.tr_acc)) { set_error("trace arrays go together"); return MCMCN_ERR_INVALID; }
+        fn<<<g.grid, g.block, g.smem, stream>>>(a);
+
+        if (partial) {
+            HyperArgs h;
+            h.P = m->n_params; h.G = m->n_groups; h.n_chains = s->n_chains; h.S = s->stride;
+            h.chain_id0 = s->chain_id0; h.theta = s->theta; h.hyper = s->hyper;
+            h.iter = i; h.seed = r->seed;
+            h.tape_zmu = r->tape_zmu ? r->tape_zmu + it * per_iter_h : nullptr;
+            h.tape_qsig = r->tape_qsig ? r->tape_qsig + it * per_iter_h : nullptr;
+            const dim3 hg((unsigned)((s->n_chains + 31) / 32), (unsigned)m->n_params, 1);
+            if (m->n_groups >= 64) hyper_kernel<8><<<hg, dim3(32, 8, 1), 0, stream>>>(h);
+            else hyper_kernel<1><<<hg, dim3(32, 1, 1), 0, stream>>>(h);
+        }
+
+        if (r->store && i >= r->burn && (i % r->thin) == 0) {
+            if (row >= r->store_rows) { set_error("sample store overflow at row %lld", (long long)row); return MCMCN_ERR_INVALID; }
+            const dim3 sg((unsigned)((s->n_chains + 127) / 128), (unsigned)ncol, 1);
+            if (ncol > 65535) { set_error("more than 65535 columns per row not supported yet"); return MCMCN_ERR_UNSUPPORTED; }
+            if (r->store_dtype == 64)
+                snapshot_kernel<double><<<sg, 128, 0, stream>>>(m->n_params, m->n_groups, partial ? 1 : 0, s->n_chains, s->stride,
+                                                                s->theta, s->hyper, (double*)r->store + (size_t)row * ncol * S);
+            else
+                snapshot_kernel<float><<<sg, 128, 0, stream>>>(m->n_params, m->n_groups, partial ? 1 : 0, s->n_chains, s->stride,
+                                                               s->theta, s->hyper, (float*)r->store + (size_t)row * ncol * S);
+            ++row;
+        }
+    }
+    CK(cudaGetLastError());
+    return MCMCN_OK;
+}
+
+int mcmcn_group_loglik(const mcmcn_model* m, const mcmcn_state* s, const double* pooled_theta, double* out_ll, void* stream_) {
+    const KernelSet* ks = nullptr;
+    int rc = validate(m, s, &ks);
+    if (rc) return rc;
+    if (!out_ll) { set_error("null output"); return MCMCN_ERR_INVALID; }
+    SweepArgs a;
+    fill_args(a, ks, m, s);
+    a.pooled_theta = pooled_theta;
+    a.out_ll = out_ll;
+    const Geometry g = geometry(ks, m, s->n_chains);
+    const sweep_fn fn = g.wide ? ks->eval_wide : ks->eval_one;
+    rc = set_smem_attr((const void*)fn, g.smem);
+    if (rc) return rc;
+    fn<<<g.grid, g.block, g.smem, (cudaStream_t)stream_>>>(a);
+    CK(cudaGetLastError());
+    return MCMCN_OK;
+}
+
+int mcmcn_pooled_nll(int n_groups, int stride, const double* ll, double* out, void* stream_) {
+    if (n_groups < 1 || stride < 1 || !ll || !out) { set_error("bad pooled_nll args"); return MCMCN_ERR_INVALID; }
+    pooled_nll_kernel<<<(stride + 127) / 128, 128, 0, (cudaStream_t)stream_>>>(n_groups, stride, ll, out);
+    CK(cudaGetLastError());
+    return MCMCN_OK;
+}
+
+int mcmcn_pointwise_loglik(const mcmcn_model* m, const mcmcn_state* s, double* out, void* stream_) {
+    const KernelSet* ks = nullptr;
+    int rc = validate(m, s, &ks);
+    if (rc) return rc;
+    if (!out) { set_error("null output"); return MCMCN_ERR_INVALID; }
+    SweepArgs a;
+    fill_args(a, ks, m, s);
+    // observation offsets per group (device scratch, built from the host table)
+    const int G = m->n_groups;
+    long long* obs_off_h = new long long[G + 1];
+    int* nobs_h = new int[G];
+    cudaError_t e = cudaMemcpy(nobs_h, m->group_nobs, sizeof(int) * G, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { delete[] obs_off_h; delete[] nobs_h; set_error("cuda: %s", cudaGetErrorString(e)); return MCMCN_ERR_CUDA; }
+    obs_off_h[0] = 0;
+    for (int g = 0; g < G; ++g) obs_off_h[g + 1] = obs_off_h[g] + nobs_h[g];
+    long long* obs_off_d = nullptr;
+    e = cudaMalloc(&obs_off_d, sizeof(long long) * (G + 1));
+    if (e == cudaSuccess) e = cudaMemcpy(obs_off_d, obs_off_h, sizeof(long long) * (G + 1), cudaMemcpyHostToDevice);
+    delete[] obs_off_h;
+    delete[] nobs_h;
+    if (e != cudaSuccess) { cudaFree(obs_off_d); set_error("cuda: %s", cudaGetErrorString(e)); return MCMCN_ERR_CUDA; }
+    const dim3 grid((unsigned)G, (unsigned)((s->n_chains + 127) / 128), 1);
+    ks->pointwise<<<grid, 128, 0, (cudaStream_t)stream_>>>(a, obs_off_d, out);
+    e = cudaStreamSynchronize((cudaStream_t)stream_);
+    cudaFree(obs_off_d);
+    if (e != cudaSuccess) { set_error("cuda: %s", cudaGetErrorString(e)); return MCMCN_ERR_CUDA; }
+    return MCMCN_OK;
+}
+
+}  // extern "C"
+
+namespace mcmcn {
+__global__ void philox_kat_kernel(const unsigned* c, const unsigned* k, unsigned* out) {
+    const uint4 r = philox4x32_10(make_uint4(c[0], c[1], c[2], c[3]), make_uint2(k[0], k[1]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+}  // namespace mcmcn
+
+extern "C" int mcmcn_debug_philox(const void* counter, const void* key, void* out) {
+    if (!counter || !key || !out) { set_error("null pointer"); return MCMCN_ERR_INVALID; }
+    philox_kat_kernel<<<1, 1>>>((const unsigned*)counter, (const unsigned*)key, (unsigned*)out);
+    CK(cudaDeviceSynchronize());
+    return MCMCN_OK;
+}

@@ -1,0 +1,107 @@
+// mcmcn_peaks.cu -- FFMA-only and MUFU-only microbenchmarks.  MEASURED_PEAKS.json holds no
+// FP32 / MUFU figure, and the step kernels are bound by exactly these two pipes
+// (SURVEY.md section 8d), so the roofline denominators are measured in the same job.
+#include <cuda_runtime.h>
+
+#include "mcmcn_host.h"
+
+namespace mcmcn {
+
+// 16 independent accumulators per thread, operands arranged like the regression hot loop
+// (one shared multiplicand, per-accumulator multiplier) so the register-bank behaviour matches.
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, float seed) {
+    float a[16], b[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { a[i] = seed + i; b[i] = 1.0f + 1e-7f * (threadIdx.x + i); }
+    float x = seed * 0.5f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = fmaf(x, b[i], a[i]);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    if (s == 12345.678f) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256) mufu_peak_kernel(float* out, int iters, float seed) {
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = seed + 0.01f * (threadIdx.x & 7) + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i];
+    if (s == 12345.678f) out[0] = s;
+}
+
+template <typename K>
+static int time_kernel(K launch, double work_per_launch, double* out, cudaStream_t stream) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int w = 0; w < 3; ++w) launch();
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(e0, stream));
+        launch();
+        CK(cudaEventRecord(e1, stream));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double rate = work_per_launch / (ms * 1e-3);
+        if (rate > best) best = rate;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CK(cudaGetLastError());
+    *out = best;
+    return MCMCN_OK;
+}
+
+}  // namespace mcmcn
+
+using namespace mcmcn;
+
+extern "C" {
+
+int mcmcn_peak_fp32(double* out_flops, void* stream_) {
+    if (!out_flops) { set_error("null output"); return MCMCN_ERR_INVALID; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int dev = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    float* d = nullptr;
+    CK(cudaMalloc(&d, 16));
+    const int iters = 4096, blocks = sms * 8, threads = 256;
+    const double flops = 2.0 * 16 * 8 * (double)iters * threads * blocks;
+    const int rc = time_kernel([&] { ffma_peak_kernel<<<blocks, threads, 0, stream>>>(d, iters, 1.0f); }, flops, out_flops, stream);
+    cudaFree(d);
+    return rc;
+}
+
+int mcmcn_peak_mufu(double* out_ops, void* stream_) {
+    if (!out_ops) { set_error("null output"); return MCMCN_ERR_INVALID; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int dev = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    float* d = nullptr;
+    CK(cudaMalloc(&d, 16));
+    const int iters = 2048, blocks = sms * 8, threads = 256;
+    const double ops = 8.0 * 8 * (double)iters * threads * blocks;
+    const int rc = time_kernel([&] { mufu_peak_kernel<<<blocks, threads, 0, stream>>>(d, iters, -1.0f); }, ops, out_ops, stream);
+    cudaFree(d);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,356 @@
+"""Host side of the GPU engine: model packing, chain state, start-up, run loop, sample store.
+
+PyTorch is used for device memory, streams and (in the callers) torch.distributed only;
+every kernel launch goes through the C ABI in include/mcmcn.h via mcmcn_native (ctypes).
+
+Reference symbols this module stands in for (``/root/reference/posteriorSampling.py``):
+  MCMC.__init__ / _findStartingPoint ....... :944-1095   -> Engine.initialise
+  StepMethod.__init__ / _setStartingPoint .. :517-592, :725-758 -> Engine.initialise
+  Sampler.sample / _loop .................... :827-896    -> Engine.run
+"""
+
+import ctypes
+import math
+
+import numpy
+import scipy.special
+import torch
+
+import mcmcn_native as nat
+from objectives import Objective
+
+_NORM_PDF_LOGC = numpy.log(numpy.sqrt(2 * numpy.pi))
+
+
+def burnThin(nIter, nSamples):
+    """posteriorSampling.py:1018-1027."""
+    if nIter < nSamples:
+        print("nIter (%i) cannot be less than nSamples (%i)." % (nIter, nSamples))
+        raise Exception()
+    elif nIter // 2 > nSamples:
+        burn = nIter // 2
+    else:
+        burn = nIter - nSamples
+    thin = int(numpy.ceil((nIter - burn) / nSamples))
+    return burn, thin
+
+
+def retainedIterations(nIter, burn, thin):
+    """Iterations whose state Sampler._loop writes out (:887)."""
+    return [i for i in range(nIter) if i % thin == 0 and i >= burn]
+
+
+def hostNormLogpdf(x, loc, scale):
+    """scipy.stats.norm(loc, scale).logpdf(x), same operation order (used for the start state)."""
+    with numpy.errstate(all="ignore"):
+        y = (x - loc) / scale
+        out = -y ** 2 / 2.0 - _NORM_PDF_LOGC - numpy.log(scale)
+        bad = ~(numpy.asarray(scale) > 0) | numpy.isnan(y)
+        return numpy.where(bad, numpy.nan, out)
+
+
+def priorFromScipy(frozen):
+    """Map a frozen scipy.stats distribution (what the reference takes in
+    ``priorDistribution``) to the device prior record."""
+    name = frozen.dist.name
+    shapes, loc, scale = frozen.dist._parse_args(*frozen.args, **frozen.kwds)
+    pr = nat.Prior()
+    pr.loc, pr.scale = float(loc), float(scale)
+    with numpy.errstate(all="ignore"):
+        pr.log_scale = float(numpy.log(float(scale)))
+    pr.a, pr.c0 = 0.0, 0.0
+    if name == "norm":
+        pr.family = nat.PRIOR_NORM
+    elif name == "gamma":
+        pr.family = nat.PRIOR_GAMMA
+        pr.a = float(shapes[0])
+        pr.c0 = float(scipy.special.gammaln(pr.a))
+    elif name == "uniform":
+        pr.family = nat.PRIOR_UNIFORM
+    elif name == "expon":
+        pr.family = nat.PRIOR_EXPON
+    elif name == "halfnorm":
+        pr.family = nat.PRIOR_HALFNORM
+    else:
+        raise ValueError("prior family %r has no device implementation "
+                         "(supported: norm, gamma, uniform, expon, halfnorm)" % name)
+    return pr
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class SampleStore(object):
+    """Retained samples on the device: [rows][ncol][S], chain fastest (include/mcmcn.h)."""
+
+    def __init__(self, engine, nRows, dtype=torch.float64):
+        self.engine = engine
+        self.nRows = int(nRows)
+        self.dtype = dtype
+        self.tensor = torch.zeros((self.nRows, engine.nCol, engine.S), dtype=dtype, device=engine.device)
+        self.iterations = []
+
+    def hostArray(self):
+        """[rows][ncol][nChains] numpy array."""
+        return self.tensor[:len(self.iterations), :, :self.engine.nChains].cpu().numpy()
+
+
+class Engine(object):
+    def __init__(self, objective, nGroups, nResponsesPerGroup, pooling, nChains,
+                 priorDistribution=None, chainId0=0, seed=0, device=None, taskObsTarget=256):
+        if not isinstance(objective, Objective):
+            raise TypeError("logLikelihoodFunction must be an Objective handle (device function); "
+                            "a Python callable cannot run on the GPU and there is no CPU fallback")
+        if pooling not in nat.POOLING_CODE:
+            raise Exception("Invalid pooling: ", pooling)
+        self.lib = nat.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("the MCMC engine needs a CUDA device; there is no CPU fallback")
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.objective = objective
+        self.pooling = pooling
+        self.P = objective.nParameters
+        self.nChains = int(nChains)
+        self.S = (self.nChains + 31) & ~31
+        self.chainId0 = int(chainId0)
+        self.seed = int(seed)
+        if type(nResponsesPerGroup) == int:
+            nResponsesPerGroup = [nResponsesPerGroup] * nGroups
+        self.nResponsesPerGroup = [int(r) for r in nResponsesPerGroup]
+        self.nObservations = int(sum(self.nResponsesPerGroup))
+        if pooling == "complete":                      # :667-671
+            self.G = 1
+            stepped = [self.nObservations]
+        else:
+            self.G = int(nGroups)
+            stepped = self.nResponsesPerGroup
+        if pooling in ("none", "complete"):            # :673-677, :693-697
+            if priorDistribution is None or self.P != len(priorDistribution):
+                raise ValueError("Invalid prior")
+        self.partial = pooling == "partial"
+        self.priorScipy = priorDistribution
+        self.nCol = self.P * (self.G + (2 if self.partial else 0))
+        if self.partial and self.G < 2:
+            raise ValueError("partial pooling needs at least 2 groups (the reference divides by nGroups - 1)")
+
+        # ---- model
+        data, group_off, group_nobs, obj_const = objective.pack(stepped)
+        elem = data.dtype.itemsize
+        cap = self.lib.mcmcn_tile_capacity_bytes() // elem
+        task_group0 = [0]
+        acc_elems, acc_obs = 0, 0
+        for g in range(self.G):
+            e = int(group_off[g + 1] - group_off[g])
+            if g > task_group0[-1] and (acc_elems + e > cap or acc_obs + int(group_nobs[g]) > taskObsTarget):
+                task_group0.append(g)
+                acc_elems, acc_obs = 0, 0
+            acc_elems += e
+            acc_obs += int(group_nobs[g])
+        task_group0.append(self.G)
+        self._group_off_h = numpy.ascontiguousarray(group_off, dtype=numpy.int64)
+        self._task_group0_h = numpy.ascontiguousarray(task_group0, dtype=numpy.int32)
+        dev = self.device
+        self._data = torch.from_numpy(data).to(dev)
+        self._group_off = torch.from_numpy(self._group_off_h).to(dev)
+        self._group_nobs = torch.from_numpy(group_nobs).to(dev)
+        self._task_group0 = torch.from_numpy(self._task_group0_h).to(dev)
+        self._obj_const = torch.from_numpy(obj_const).to(dev) if obj_const is not None else None
+
+        m = nat.Model()
+        m.objective = objective.kind
+        m.n_params = self.P
+        m.n_coef = objective.nCoef
+        m.precision = 32 if objective.precision == "fp32" else 64
+        m.pooling = nat.POOLING_CODE[pooling]
+        m.n_groups = self.G
+        m.n_tasks = len(task_group0) - 1
+        m.n_obj_const = 0 if obj_const is None else len(obj_const)
+        m.n_obs = self.nObservations
+        m.data = _ptr(self._data)
+        m.group_off = _ptr(self._group_off)
+        m.group_nobs = _ptr(self._group_nobs)
+        m.task_group0 = _ptr(self._task_group0)
+        m.task_group0_host = self._task_group0_h.ctypes.data_as(ctypes.c_void_p)
+        m.group_off_host = self._group_off_h.ctypes.data_as(ctypes.c_void_p)
+        m.obj_const = _ptr(self._obj_const)
+        m.user_objective = objective.userHandle
+        if not self.partial:
+            for p, d in enumerate(priorDistribution):
+                m.prior[p] = priorFromScipy(d)
+        self.model = m
+        if objective.kind != nat.OBJ_USER and not self.lib.mcmcn_supported(
+                m.objective, m.n_params, m.n_coef, m.precision):
+            raise RuntimeError("objective kind %d with %d parameters (%d coefficients) at %s is not compiled "
+                               "into libmcmcn.so" % (m.objective, m.n_params, m.n_coef, objective.precision))
+
+        # ---- chain state
+        P, G, S = self.P, self.G, self.S
+        f64 = torch.float64
+        self.theta = torch.zeros((P, G, S), dtype=f64, device=dev)
+        self.scale = torch.ones((P, G, S), dtype=f64, device=dev)            # :269
+        self.counts = torch.zeros((P, G, S), dtype=torch.int32, device=dev)
+        self.ll = torch.full((G, S), float("nan"), dtype=f64, device=dev)    # :265
+        self.lprior = torch.zeros((P, G, S), dtype=f64, device=dev)
+        self.hyper = torch.zeros((4, P, S), dtype=f64, device=dev) if self.partial else None
+        self.lpriorStale = False
+        st = nat.State()
+        st.n_chains = self.nChains
+        st.stride = S
+        st.chain_id0 = self.chainId0
+        st.theta, st.scale, st.counts = _ptr(self.theta), _ptr(self.scale), _ptr(self.counts)
+        st.ll, st.lprior, st.hyper = _ptr(self.ll), _ptr(self.lprior), _ptr(self.hyper)
+        self.state = st
+
+    # ------------------------------------------------------------------ helpers
+    @property
+    def stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _up(self, dst, src, lastAxisChains=True):
+        """Copy a host array whose last axis is the chain into a [.., S] device tensor."""
+        t = torch.from_numpy(numpy.ascontiguousarray(src)).to(self.device)
+        dst[..., :self.nChains].copy_(t.to(dst.dtype))
+
+    def setHyper(self, mu, sigma2):
+        """mu, sigma2: [P][nChains] host arrays."""
+        mu = numpy.asarray(mu, dtype=float)
+        sigma2 = numpy.asarray(sigma2, dtype=float)
+        with numpy.errstate(all="ignore"):
+            sd = numpy.sqrt(sigma2)
+            lsd = numpy.log(sd)
+        self._up(self.hyper, numpy.stack([mu, sigma2, sd, lsd]))
+
+    def setState(self, theta, ll, lprior=None, mu=None, sigma2=None, scale=None, counts=None):
+        """Host arrays with the chain as LAST axis: theta/lprior/scale [P][G][nC], ll [G][nC]."""
+        self._up(self.theta, theta)
+        self._up(self.ll, ll)
+        if lprior is not None:
+            self._up(self.lprior, lprior)
+        if scale is not None:
+            self._up(self.scale, scale)
+        if counts is not None:
+            self._up(self.counts, counts)
+        if self.partial:
+            self.setHyper(mu, sigma2)
+
+    def getState(self):
+        n = self.nChains
+        out = {"theta": self.theta[..., :n].cpu().numpy(), "ll": self.ll[..., :n].cpu().numpy(),
+               "scale": self.scale[..., :n].cpu().numpy(), "lprior": self.lprior[..., :n].cpu().numpy()}
+        if self.partial:
+            h = self.hyper[..., :n].cpu().numpy()
+            out["mu"], out["sigma2"] = h[0], h[1]
+        return out
+
+    # ------------------------------------------------------------------ evaluation
+    def groupLogLikelihood(self, pooledTheta=None):
+        """[G][S] device tensor of group log-likelihoods of the current state, or of
+        ``pooledTheta`` ([P][nChains] host array: every group uses the same values)."""
+        out = torch.empty((self.G, self.S), dtype=torch.float64, device=self.device)
+        pt = None
+        if pooledTheta is not None:
+            pt = torch.zeros((self.P, self.S), dtype=torch.float64, device=self.device)
+            self._up(pt, pooledTheta)
+        nat.call("mcmcn_group_loglik", ctypes.byref(self.model), ctypes.byref(self.state),
+                 _ptr(pt), _ptr(out), self.stream)
+        return out
+
+    def pooledNll(self, x):
+        """MCMC._mleObjectiveFunction (:1102-1105) for every chain: x is [P][nChains]."""
+        ll = self.groupLogLikelihood(x)
+        out = torch.empty((self.S,), dtype=torch.float64, device=self.device)
+        nat.call("mcmcn_pooled_nll", self.G, self.S, _ptr(ll), _ptr(out), self.stream)
+        return out[:self.nChains].cpu().numpy()
+
+    def pointwiseLogLikelihood(self):
+        """StepMethod.logLikelihood (:656-659): [N][nChains] host array."""
+        out = torch.empty((self.nObservations, self.S), dtype=torch.float64, device=self.device)
+        nat.call("mcmcn_pointwise_loglik", ctypes.byref(self.model), ctypes.byref(self.state),
+                 _ptr(out), self.stream)
+        return out[:, :self.nChains].cpu().numpy()
+
+    # ------------------------------------------------------------------ start-up
+    def initialise(self, parameterName, startingPointValueRange=None, startWithMLE=False, logger=None):
+        """Reference start-up, all chains at once.  Each chain draws from its own legacy
+        MT19937 stream seeded with its global chain id (seed = chain, :225, :1015), in the
+        reference's order, so start states equal the reference's."""
+        from startpoint import findStartingPoints
+        P, G, nC = self.P, self.G, self.nChains
+        rss = [numpy.random.RandomState(self.chainId0 + c) for c in range(nC)]
+        x = findStartingPoints(self, rss, parameterName, startingPointValueRange, startWithMLE, logger)
+        self.startingPoint = x                                   # [P][nC]
+
+        theta = numpy.zeros((P, G, nC))
+        if not self.partial:                                     # :584-592
+            lprior = numpy.zeros((P, G, nC))
+            for p in range(P):
+                theta[p, :, :] = x[p][None, :]
+                with numpy.errstate(all="ignore"):
+                    lprior[p, :, :] = numpy.asarray(self.priorScipy[p].logpdf(x[p]), dtype=float)[None, :]
+            self.setState(theta, numpy.full((G, nC), numpy.nan), lprior)
+            return
+
+        # partial pooling, :725-758
+        mu = x.copy()
+        sigma2 = numpy.sqrt(numpy.abs(x) / 10.)                  # sic (:730)
+        sd = numpy.sqrt(sigma2)
+        for c in range(nC):
+            for p in range(P):
+                theta[p, :, c] = rss[c].standard_normal(G) * sd[p, c] + mu[p, c]
+        lprior = hostNormLogpdf(theta, mu[:, None, :], sd[:, None, :])
+        self.setState(theta, numpy.full((G, nC), numpy.nan), lprior, mu, sigma2)
+        ll = numpy.full((G, nC), numpy.nan)
+        for attempt in range(100000):
+            cur = self.groupLogLikelihood()[:, :nC].cpu().numpy()
+            fin = numpy.isfinite(cur)
+            ll[fin] = cur[fin]
+            if fin.all():
+                break
+            for c in numpy.nonzero(~fin.all(axis=0))[0]:
+                bad = numpy.nonzero(~fin[:, c])[0]
+                for p in range(P):                               # log-prior left stale, :284-288
+                    theta[p, bad, c] = rss[c].standard_normal(len(bad)) * sd[p, c] + mu[p, c]
+            self.lpriorStale = True
+            self._up(self.theta, theta)
+        else:
+            raise RuntimeError("could not find finite group log-likelihoods for every group")
+        self._up(self.ll, ll)
+
+    # ------------------------------------------------------------------ run loop
+    def run(self, iter0, nIter, burn, thin, store=None, tape=None, trace=False,
+            tuneInterval=100, useLpriorOverride=None):
+        """Advance every chain by nIter iterations (Sampler._loop, :862-896)."""
+        P, G, S = self.P, self.G, self.S
+        a = nat.RunArgs()
+        a.iter0, a.n_iter, a.burn, a.thin = int(iter0), int(nIter), int(burn), int(thin)
+        a.tune_interval = int(tuneInterval)
+        a.seed = self.seed
+        keep = [tape]
+        if tape is not None:
+            a.tape_z, a.tape_u = _ptr(tape["z"]), _ptr(tape["u"])
+            a.tape_accept = _ptr(tape.get("accept"))
+            a.tape_zmu, a.tape_qsig = _ptr(tape.get("zmu")), _ptr(tape.get("qsig"))
+        tr = None
+        if trace:
+            shape = (nIter, P, G, S)
+            tr = {"ll": torch.zeros(shape, dtype=torch.float64, device=self.device),
+                  "lp": torch.zeros(shape, dtype=torch.float64, device=self.device),
+                  "diff": torch.zeros(shape, dtype=torch.float64, device=self.device),
+                  "accept": torch.zeros(shape, dtype=torch.uint8, device=self.device)}
+            a.trace_ll, a.trace_lp, a.trace_diff = _ptr(tr["ll"]), _ptr(tr["lp"]), _ptr(tr["diff"])
+            a.trace_accept = _ptr(tr["accept"])
+        if store is not None:
+            a.store = _ptr(store.tensor)
+            a.store_dtype = 64 if store.dtype == torch.float64 else 32
+            a.store_row0 = len(store.iterations)
+            a.store_rows = store.nRows
+            store.iterations += [i for i in range(iter0, iter0 + nIter) if i % thin == 0 and i >= burn]
+        if useLpriorOverride is None:
+            useLpriorOverride = self.partial and self.lpriorStale and iter0 == 0
+        a.use_lprior_override = 1 if useLpriorOverride else 0
+        nat.call("mcmcn_run", ctypes.byref(self.model), ctypes.byref(self.state), ctypes.byref(a), self.stream)
+        if iter0 == 0 and nIter > 0:
+            self.lpriorStale = False
+        del keep
+        return tr

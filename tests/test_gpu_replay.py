@@ -1,0 +1,117 @@
+"""GPU parity tests proper (north star "Equivalence"): tape-driven replay of the CUDA step
+kernels against the CPU oracle, through the C ABI.
+
+  * per-step proposal log-likelihood within 1e-5 relative (FP32 objective math) /
+    1e-11 (FP64), proposal log-prior within 1e-12;
+  * accept/reject trajectory identical; in FP32 mode the oracle's decisions are
+    teacher-forced and any decision the engine would have taken differently must be a
+    documented near-threshold tie (|log u - diff| <= 1e-4 * max(|ll|, 1));
+  * retained rows equal the oracle's (FP64: to 1e-9 and as "%f" text).
+"""
+
+import numpy
+import pytest
+import scipy.stats
+
+from conftest import loadGolden, oracleObjectiveFromMeta
+import parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _goldenCase(case):
+    meta = loadGolden(case)
+    obj, prior = oracleObjectiveFromMeta(meta)
+    return meta, obj, prior
+
+
+def _fmt(rows):
+    return [",".join("%f" % v for v in r) for r in rows]
+
+
+@pytest.mark.parametrize("case", ["reg_partial", "reg_none", "reg_complete", "dist_none",
+                                  "dist_complete", "c1_distribution_partial", "reg_ragged_partial"])
+def test_replay_fp64_is_trajectory_exact(case):
+    meta, obj, prior = _goldenCase(case)
+    nIter, nSamples = 300, 100
+    res = parity.replay(obj, tuple(meta["parameterName"]), meta["nGroups"], meta["nResponsesPerGroup"],
+                        meta["pooling"], prior, meta["startingPointValueRange"], nChains=3,
+                        nIter=nIter, nSamples=nSamples, precision="fp64", force=False)
+    err, ties = parity.checkReplay(res, 1e-11, 0.0)
+    assert ties == 0
+    numpy.testing.assert_allclose(res.final["theta"], res.oracleFinal, rtol=1e-12, atol=1e-12)
+    numpy.testing.assert_allclose(res.rows, res.oracleRows, rtol=1e-9, atol=1e-9)
+    for c in range(3):   # the sample file text the CSV writer would emit
+        assert _fmt(res.rows[:, :, c]) == _fmt(res.oracleRows[:, :, c])
+
+
+@pytest.mark.parametrize("case", ["reg_partial", "reg_none", "reg_complete", "dist_none",
+                                  "c1_distribution_partial", "reg_ragged_partial"])
+def test_replay_fp32_log_density_and_ties(case):
+    meta, obj, prior = _goldenCase(case)
+    res = parity.replay(obj, tuple(meta["parameterName"]), meta["nGroups"], meta["nResponsesPerGroup"],
+                        meta["pooling"], prior, meta["startingPointValueRange"], nChains=4,
+                        nIter=300, nSamples=100, precision="fp32")
+    err, ties = parity.checkReplay(res, 1e-5, 1e-4)
+    decisions = res.oracle["accept"].size
+    assert ties <= max(3, decisions // 2000), "too many ties: %d of %d" % (ties, decisions)
+    # teacher-forced, so the state follows the oracle exactly (proposals are FP64)
+    numpy.testing.assert_allclose(res.final["theta"], res.oracleFinal, rtol=1e-12, atol=1e-12)
+    numpy.testing.assert_allclose(res.rows, res.oracleRows, rtol=1e-9, atol=1e-9)
+
+
+def test_replay_mle_start_regression_example():
+    """C2: example.regression with startWithMLE (oracle start state fed to the engine)."""
+    meta, obj, prior = _goldenCase("reg_partial")
+    res = parity.replay(obj, tuple(meta["parameterName"]), 10, 10, "partial", prior,
+                        meta["startingPointValueRange"], nChains=2, nIter=400, nSamples=100,
+                        precision="fp64", force=False, startWithMLE=True)
+    err, ties = parity.checkReplay(res, 1e-11, 0.0)
+    assert ties == 0
+    numpy.testing.assert_allclose(res.rows, res.oracleRows, rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("fp64", 1e-11)])
+def test_replay_c3_shape_wide_path(precision, tol):
+    """C3's shape (K = 8 coefficients + sigma, R = 200) on the 4-chains-per-lane kernel,
+    with a chain count that leaves partial warps."""
+    obj, names, nResp, ranges = parity.syntheticRegression(G=6, R=200, K=8)
+    res = parity.replay(obj, names, 6, nResp, "partial", None, ranges, nChains=133, nIter=25,
+                        nSamples=10, precision=precision)
+    err, ties = parity.checkReplay(res, tol, 1e-4)
+    numpy.testing.assert_allclose(res.rows, res.oracleRows, rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("pooling", ["partial", "none"])
+def test_replay_bernoulli_logit(pooling):
+    obj, names, nResp, ranges = parity.syntheticLogit(G=30, R=50)
+    prior = [scipy.stats.norm(0, 5), scipy.stats.norm(0, 5)] if pooling == "none" else None
+    res = parity.replay(obj, names, 30, nResp, pooling, prior, ranges, nChains=5, nIter=120,
+                        nSamples=40, precision="fp32")
+    err, ties = parity.checkReplay(res, 1e-5, 1e-4)
+    res64 = parity.replay(obj, names, 30, nResp, pooling, prior, ranges, nChains=2, nIter=120,
+                          nSamples=40, precision="fp64", force=False)
+    err64, ties64 = parity.checkReplay(res64, 1e-11, 0.0)
+    assert ties64 == 0
+
+
+def test_replay_streaming_group_larger_than_tile():
+    """Complete pooling makes one group of all N observations; with N beyond the shared-memory
+    tile the block is streamed through it by repeated TMA copies."""
+    obj, names, nResp, ranges = parity.syntheticRegression(G=50, R=100, K=2)
+    prior = [scipy.stats.norm(0, 10), scipy.stats.norm(0, 10), scipy.stats.gamma(2)]
+    res = parity.replay(obj, names, 50, nResp, "complete", prior, ranges, nChains=3, nIter=40,
+                        nSamples=20, precision="fp32")
+    err, ties = parity.checkReplay(res, 1e-5, 1e-4)
+    res = parity.replay(obj, names, 50, nResp, "complete", prior, ranges, nChains=2, nIter=40,
+                        nSamples=20, precision="fp64", force=False)
+    parity.checkReplay(res, 1e-11, 0.0)
+
+
+def test_ragged_groups_and_prior_families():
+    obj, names, nResp, ranges = parity.syntheticRegression(G=9, R=7, K=2, ragged=True)
+    prior = [scipy.stats.uniform(-20, 40), scipy.stats.expon(-6, 4), scipy.stats.halfnorm(0, 3)]
+    res = parity.replay(obj, names, 9, nResp, "none", prior, ranges, nChains=3, nIter=150,
+                        nSamples=50, precision="fp64", force=False)
+    err, ties = parity.checkReplay(res, 1e-11, 0.0)
+    assert ties == 0
