@@ -16,7 +16,7 @@
  * Layout conventions (S = mcmcn_state.stride, the padded chain count):
  *   per-(name, group, chain) arrays are [P][G][S] with the chain index fastest,
  *   so that a warp of 32 chains reads/writes 256 contiguous bytes;
- *   per-(group, chain) arrays are [G][S]; hyper-parameters are [4][P][S].
+ *   per-(group, chain) arrays are [G][S]; hyper-parameters are [5][P][S].
  */
 #ifndef MCMCN_H
 #define MCMCN_H
@@ -80,8 +80,8 @@ typedef struct mcmcn_prior {
  * `data` holds one packed block per group, group g at element offset
  * group_off[g] (group_off has G+1 entries; elements are float when
  * precision == 32 and double when precision == 64).  Block layouts:
- *   linear_regression   ceil(R/4) quads of [4 obs][KP] x then [4] e, KP = K rounded up to 4;
- *                       e = y - x.bbar_g with bbar_g the group's reference point, obj_const[g*K+k]
+ *   linear_regression   ceil(R/4) quads of [KP][4 obs] x then [4] ne, KP = K rounded up to 4;
+ *                       ne = x.bbar_g - y with bbar_g the group's reference point, obj_const[g*K+k]
  *   bernoulli_logit     ceil(R/4) quads of [4] x then [4] y
  *   gaussian_distribution  ceil(R/4) quads of [4 obs][PP] mu_j of the observation's group, PP = P rounded up to 4
  * (padding observations are zero).  Tasks are runs of consecutive groups
@@ -120,7 +120,7 @@ typedef struct mcmcn_state {
     uint32_t* counts;        /* [P][G][S] nAccepted | nRejected << 16 since the last tune */
     double* ll;              /* [G][S]    group log-likelihood (NaN = never set, :265) */
     double* lprior;          /* [P][G][S] Parameter._logPrior (fixed priors; partial: iteration-0 override, may be NULL) */
-    double* hyper;           /* [4][P][S] mu, sigma2, sqrt(sigma2), log sqrt(sigma2) (partial pooling) */
+    double* hyper;           /* [5][P][S] mu, sigma2, sd = sqrt(sigma2), log sd, 1/sd (partial pooling) */
 } mcmcn_state;
 
 /* One call advances all chains by n_iter iterations of Sampler._loop
@@ -149,6 +149,11 @@ typedef struct mcmcn_run_args {
     int32_t use_lprior_override; /* partial pooling: read the current log-prior from state.lprior (iteration iter0 only) */
     int64_t store_row0;          /* row that the first retained iteration of this call goes to */
     int64_t store_rows;          /* capacity in rows */
+    /* optional per-kernel timing (host pointer to 8 doubles, accumulated into; NULL = off):
+     * [0] step-kernel ms, [1] hyper-kernel ms, [2] write-back ms, [3] step launches,
+     * [4] hyper launches, [5] write-back launches.  When set, every launch is bracketed by
+     * CUDA events on `stream` and the call synchronises before returning. */
+    double* timing;
 } mcmcn_run_args;
 
 int mcmcn_version(void);

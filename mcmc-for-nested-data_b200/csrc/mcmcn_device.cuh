@@ -81,14 +81,25 @@ __device__ __forceinline__ uint4 philox_draw(long long chain_id, unsigned long l
     const uint2 key = make_uint2((unsigned)chain_id ^ (unsigned)(seed >> 32) * 0x9E3779B1u, (unsigned)seed ^ (unsigned)(chain_id >> 32));
     return philox4x32_10(ctr, key);
 }
-// standard normal from two 32-bit words (Box-Muller, fp32 resolution; symmetric about 0)
+// standard normal from two 32-bit words (Box-Muller at fp32 resolution on the MUFU unit:
+// lg2, rsq-based sqrt, cos; symmetric about 0, |z| <= 5.8)
 __device__ __forceinline__ double normal_from(unsigned a, unsigned b) {
     const float u1 = (float)((a >> 8) + 1u) * 5.9604644775390625e-8f;   // (0, 1]
     const float u2 = (float)(b >> 8) * 5.9604644775390625e-8f;          // [0, 1)
-    const float r = sqrtf(-2.0f * logf(u1));
-    float s, c;
-    sincospif(2.0f * u2, &s, &c);
-    return (double)(r * c);
+    const float r = sqrtf(-2.0f * __logf(u1));
+    return (double)(r * __cosf(6.283185307179586f * u2));
+}
+// log(u) < diff, decided in FP32 when the margin allows and in FP64 otherwise.  __logf is
+// accurate to 2^-21.41 absolute on [0.5, 2] and 3 ulp elsewhere; (float)u adds 6e-8 relative,
+// so |__logf((float)u) - log(u)| < 1e-6 * (1 + |log u|) with a wide margin.
+__device__ __forceinline__ bool log_u_less_than(double u, double diff) {
+    const float lu = __logf((float)u);
+    const float tol = 1e-6f * (1.0f + fabsf(lu));
+    const float d = (float)diff;                      // rounding of diff: relative 6e-8, inside tol for |diff| ~ |lu|
+    const float dtol = 1.2e-7f * fabsf(d);
+    if (d - dtol > lu + tol) return true;
+    if (d + dtol < lu - tol) return false;
+    return log(u) < diff;
 }
 // uniform in [0,1) with 53 random bits, numpy's recipe (legacy random_sample)
 __device__ __forceinline__ double uniform_from(unsigned a, unsigned b) {
@@ -101,6 +112,14 @@ __device__ __forceinline__ double norm_logpdf(double x, double loc, double scale
     const double y = __ddiv_rn(__dsub_rn(x, loc), scale);
     const double r = __dsub_rn(__dsub_rn(-0.5 * __dmul_rn(y, y), MCMCN_LOG_SQRT_2PI), log_scale);
     return (!(scale > 0.0) || y != y) ? __longlong_as_double(0x7ff8000000000000LL) : r;
+}
+// same with the reciprocal of the scale precomputed (group-level prior of partial pooling: two
+// evaluations per decision; differs from the quotient form by at most 1 ulp of y)
+__device__ __forceinline__ double norm_logpdf_inv(double x, double loc, double inv_scale, double log_scale) {
+    const double y = __dmul_rn(__dsub_rn(x, loc), inv_scale);
+    const double r = __dsub_rn(__dsub_rn(-0.5 * __dmul_rn(y, y), MCMCN_LOG_SQRT_2PI), log_scale);
+    return (!(inv_scale > 0.0) || !(inv_scale < __longlong_as_double(0x7ff0000000000000LL)) || y != y)
+               ? norm_logpdf(x, loc, 1.0 / inv_scale, log_scale) : r;
 }
 __device__ __forceinline__ double prior_logpdf(const mcmcn_prior& pr, double x) {
     const double ninf = __longlong_as_double(0xfff0000000000000LL);
@@ -159,14 +178,39 @@ template <> struct Vec4<double> {
 __device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
 __device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
 
+// Packed FP32x2 FMA (PTX fma.rn.f32x2, SASS FFMA2; new on sm_100).  A 64-bit operand is an
+// aligned even/odd register pair, so an FFMA2 with one operand served from the reuse cache
+// reads exactly one register per bank per FMA: measured 116.7 FMA lanes/clk/SM on B200 whatever
+// registers ptxas picks, against 98.4 for scalar FFMA in the same x*b[c]+r[c] pattern (the second
+// and third source collide in the even/odd bank about one time in three) and 124.6 for the
+// pipe itself (tools/fma_probe.cu).  It also halves the issue slots the FMAs take.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ float sum2(f32x2 v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return lo + hi;
+}
+
 // Linear regression with K coefficients and a noise sd (example/regression.py:53-67):
 //   ll_i = norm(loc=y_i, scale=sigma).logpdf(x_i . b)
-// Block: ceil(R/4) quads of [4 obs][KP] x followed by [4] e.
+// Block: ceil(R/4) quads of [KP][4 obs] x (coefficient-major, so one 128-bit shared load is
+// two observation pairs of one coefficient) followed by [4] ne.  Padding observations are
+// all-zero and contribute exactly 0.
 // FP32 conditioning: the residual x_i.b - y_i cancels catastrophically when |y| >> |residual|
 // (the reference's own example has |y| ~ 300 against residuals ~ 1).  The host therefore
 // centres every group on a reference point bbar_g (its least-squares fit, FP64, in
-// obj_const[g*K + k]) and stores e_i = y_i - x_i.bbar_g instead of y_i; the kernel evaluates
-// the identical residual as x_i.(b - bbar_g) - e_i with (b - bbar_g) formed in FP64.
+// obj_const[g*K + k]) and stores ne_i = x_i.bbar_g - y_i instead of y_i; the kernel evaluates
+// the identical residual as x_i.(b - bbar_g) + ne_i with (b - bbar_g) formed in FP64.
 template <int K_>
 struct LinReg {
     static constexpr int K = K_;
@@ -182,71 +226,90 @@ struct LinReg {
         return (T)(p < K ? __dsub_rn(v, cst[(size_t)g * K + p]) : v);
     }
 
-    template <int C, typename T>
-    __device__ static __forceinline__ void accumulate(const T* __restrict__ blk, int nobs, const double*,
-                                                      const T (&th)[C][P], double (&acc)[C]) {
-        const int nq = nobs >> 2;
-        for (int q = 0; q < nq; ++q) {
-            const T* xq = blk + (size_t)q * UNIT;
-            T y4[4];
-            Vec4<T>::load(xq + 4 * KP, y4);
-            T s[C];
+    // FP32 hot loop: sum of squared residuals of C chains over the block, two observations per FFMA2.
+    template <int C>
+    __device__ static __forceinline__ void accumulate(const float* __restrict__ blk, int nobs, const double*,
+                                                      const float (&th)[C][P], double (&acc)[C]) {
+        f32x2 th2[C][K];
 #pragma unroll
-            for (int c = 0; c < C; ++c) s[c] = (T)0;
+        for (int c = 0; c < C; ++c)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                T x[KP];
+            for (int k = 0; k < K; ++k) th2[c][k] = pack2(th[c][k], th[c][k]);
+        const int nq = (nobs + 3) >> 2;
+        for (int q0 = 0; q0 < nq; q0 += 2) {
+            f32x2 s2[C];
 #pragma unroll
-                for (int k4 = 0; k4 < KP; k4 += 4) {
-                    T v[4];
-                    Vec4<T>::load(xq + j * KP + k4, v);
-                    x[k4] = v[0]; x[k4 + 1] = v[1]; x[k4 + 2] = v[2]; x[k4 + 3] = v[3];
-                }
+            for (int c = 0; c < C; ++c) s2[c] = 0ull;
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    T r = -y4[j];
+            for (int u = 0; u < 2; ++u) {
+                if (q0 + u < nq) {
+                    const float* xq = blk + (size_t)(q0 + u) * UNIT;
+                    const ulonglong2 ne = *reinterpret_cast<const ulonglong2*>(xq + 4 * KP);
+                    f32x2 r[C][2];
 #pragma unroll
-                    for (int k = 0; k < K; ++k) r = fma_t(x[k], th[c][k], r);
-                    s[c] = fma_t(r, r, s[c]);
-                }
-            }
+                    for (int k = 0; k < K; ++k) {
+                        const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(xq + 4 * k);
 #pragma unroll
-            for (int c = 0; c < C; ++c) acc[c] += (double)s[c];
-        }
-        const int rem = nobs & 3;
-        if (rem) {
-            const T* xq = blk + (size_t)nq * UNIT;
-            T s[C];
+                        for (int c = 0; c < C; ++c) r[c][0] = ffma2(x.x, th2[c][k], k == 0 ? ne.x : r[c][0]);
 #pragma unroll
-            for (int c = 0; c < C; ++c) s[c] = (T)0;
-            for (int j = 0; j < rem; ++j) {
-                const T y = xq[4 * KP + j];
+                        for (int c = 0; c < C; ++c) r[c][1] = ffma2(x.y, th2[c][k], k == 0 ? ne.y : r[c][1]);
+                    }
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    T r = -y;
-#pragma unroll
-                    for (int k = 0; k < K; ++k) r = fma_t(xq[j * KP + k], th[c][k], r);
-                    s[c] = fma_t(r, r, s[c]);
+                    for (int c = 0; c < C; ++c) {
+                        s2[c] = ffma2(r[c][0], r[c][0], s2[c]);
+                        s2[c] = ffma2(r[c][1], r[c][1], s2[c]);
+                    }
                 }
             }
 #pragma unroll
-            for (int c = 0; c < C; ++c) acc[c] += (double)s[c];
+            for (int c = 0; c < C; ++c) acc[c] += (double)sum2(s2[c]);   // FP64 fold every 8 observations
         }
     }
+    // FP64 path (replay verification): same layout, scalar FMAs.
+    template <int C>
+    __device__ static __forceinline__ void accumulate(const double* __restrict__ blk, int nobs, const double*,
+                                                      const double (&th)[C][P], double (&acc)[C]) {
+        const int nq = (nobs + 3) >> 2;
+        for (int q = 0; q < nq; ++q) {
+            const double* xq = blk + (size_t)q * UNIT;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    double r = xq[4 * KP + j];
+#pragma unroll
+                    for (int k = 0; k < K; ++k) r = fma(xq[4 * k + j], th[c][k], r);
+                    acc[c] = fma(r, r, acc[c]);
+                }
+            }
+        }
+    }
+    // Per-chain terms that only change when sigma does: -1/(2 sigma^2) and R*(log sigma + log sqrt(2 pi)).
+    struct Aux { double mhalf_inv2, rlog; };
     template <typename T>
-    __device__ static __forceinline__ double finish(double acc, int R, const double*, const T (&th)[P]) {
+    __device__ static __forceinline__ Aux aux(int R, const T (&th)[P]) {
         const double sg = (double)th[K];
-        if (!(sg > 0.0)) return __longlong_as_double(0x7ff8000000000000LL);   // scipy: scale <= 0 -> nan
-        const double inv = 1.0 / sg;
-        return -0.5 * acc * inv * inv - (double)R * (log(sg) + MCMCN_LOG_SQRT_2PI);
+        Aux a;
+        if (!(sg > 0.0)) {                                    // scipy: scale <= 0 -> nan
+            a.mhalf_inv2 = a.rlog = __longlong_as_double(0x7ff8000000000000LL);
+        } else {
+            const double inv = 1.0 / sg;
+            a.mhalf_inv2 = -0.5 * inv * inv;
+            a.rlog = (double)R * (log(sg) + MCMCN_LOG_SQRT_2PI);
+        }
+        return a;
+    }
+    __device__ static __forceinline__ bool aux_depends_on(int p) { return p == K; }
+    __device__ static __forceinline__ double finish(double acc, const Aux& a) {
+        return acc * a.mhalf_inv2 - a.rlog;
     }
     template <typename T>
     __device__ static __forceinline__ double pointwise(const T* __restrict__ blk, int i, const double*, const T (&th)[P]) {
         const T* xq = blk + (size_t)(i >> 2) * UNIT;
         const int j = i & 3;
-        T r = -xq[4 * KP + j];
+        T r = xq[4 * KP + j];
 #pragma unroll
-        for (int k = 0; k < K; ++k) r = fma_t(xq[j * KP + k], th[k], r);
+        for (int k = 0; k < K; ++k) r = fma_t(xq[4 * k + j], th[k], r);
         const double sg = (double)th[K];
         if (!(sg > 0.0)) return __longlong_as_double(0x7ff8000000000000LL);
         const double z = (double)r / sg;
@@ -303,8 +366,11 @@ struct Logit {
             }
         }
     }
+    struct Aux {};
     template <typename T>
-    __device__ static __forceinline__ double finish(double acc, int, const double*, const T (&)[P]) { return acc; }
+    __device__ static __forceinline__ Aux aux(int, const T (&)[P]) { return Aux(); }
+    __device__ static __forceinline__ bool aux_depends_on(int) { return false; }
+    __device__ static __forceinline__ double finish(double acc, const Aux&) { return acc; }
     template <typename T>
     __device__ static __forceinline__ double pointwise(const T* __restrict__ blk, int i, const double*, const T (&th)[P]) {
         const T* xq = blk + (size_t)(i >> 2) * UNIT;
@@ -349,8 +415,11 @@ struct GaussDist {
             for (int c = 0; c < C; ++c) acc[c] = __dadd_rn(acc[c], (double)row<T>(rec, cst, th[c]));
         }
     }
+    struct Aux {};
     template <typename T>
-    __device__ static __forceinline__ double finish(double acc, int, const double*, const T (&)[P]) { return acc; }
+    __device__ static __forceinline__ Aux aux(int, const T (&)[P]) { return Aux(); }
+    __device__ static __forceinline__ bool aux_depends_on(int) { return false; }
+    __device__ static __forceinline__ double finish(double acc, const Aux&) { return acc; }
     template <typename T>
     __device__ static __forceinline__ double pointwise(const T* __restrict__ blk, int i, const double* cst, const T (&th)[P]) {
         return (double)row<T>(blk + (size_t)(i >> 2) * UNIT + (i & 3) * PP, cst, th);
@@ -409,16 +478,15 @@ __device__ __forceinline__ void stage_tile(T* tile, const T* src, long long elem
     parity ^= 1u;
 }
 
-// Group log-likelihood for C chains; the group's block is either resident in
-// the tile (blk != NULL) or streamed through it in chunks.
+// Group accumulators (Obj::finish turns them into log-likelihoods) for C chains; the group's
+// block is either resident in the tile (blk != NULL) or streamed through it in chunks.
 template <class Obj, int C, typename T>
 __device__ __forceinline__ void group_loglik(const SweepArgs& a, const T* blk, T* tile, int g, int R, unsigned mb,
-                                             unsigned& parity, const T (&th)[C][Obj::P], double (&out)[C]) {
-    double acc[C];
+                                             unsigned& parity, const T (&th)[C][Obj::P], double (&acc)[C]) {
 #pragma unroll
     for (int c = 0; c < C; ++c) acc[c] = 0.0;
     if (blk != nullptr) {
-        Obj::template accumulate<C, T>(blk + Obj::HDR, R, a.obj_const, th, acc);
+        Obj::template accumulate<C>(blk + Obj::HDR, R, a.obj_const, th, acc);
     } else {
         // streaming: header stays out of the tile (objectives with a header always fit)
         const T* src = reinterpret_cast<const T*>(a.data) + a.group_off[g] + Obj::HDR;
@@ -428,11 +496,9 @@ __device__ __forceinline__ void group_loglik(const SweepArgs& a, const T* blk, T
             const int n = min(chunk_obs, R - o);
             const long long elems = (long long)((n + Obj::OBS_PER_UNIT - 1) / Obj::OBS_PER_UNIT) * Obj::UNIT;
             stage_tile<T>(tile, src + (long long)(o / Obj::OBS_PER_UNIT) * Obj::UNIT, elems, mb, parity, true);
-            Obj::template accumulate<C, T>(tile, n, a.obj_const, th, acc);
+            Obj::template accumulate<C>(tile, n, a.obj_const, th, acc);
         }
     }
-#pragma unroll
-    for (int c = 0; c < C; ++c) out[c] = Obj::template finish<T>(acc[c], R, a.obj_const, th[c]);
 }
 
 // ---------------------------------------------------------------- the step kernel
@@ -466,6 +532,7 @@ __global__ void __launch_bounds__(256, MINB) sweep_kernel(const SweepArgs a) {
 
         T th[C][P];
         double llcur[C];
+        typename Obj::Aux aux_cur[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const int ch = cbase + 32 * c;
@@ -474,19 +541,20 @@ __global__ void __launch_bounds__(256, MINB) sweep_kernel(const SweepArgs a) {
             for (int p = 0; p < P; ++p)
                 th[c][p] = on ? Obj::template local<T>(p, a.theta[((size_t)p * a.G + g) * S + ch], a.obj_const, g) : (T)1;
             llcur[c] = on ? a.ll[(size_t)g * S + ch] : 0.0;
+            aux_cur[c] = Obj::template aux<T>(R, th[c]);
         }
 
 #pragma unroll 1
         for (int p = 0; p < P; ++p) {
             const size_t row = ((size_t)p * a.G + g) * S;
-            double cur[C], prop[C], sc[C], uu[C];
+            double prop[C], uu[C];
             T old[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 const int ch = cbase + 32 * c;
                 const bool on = ch < a.n_chains;
-                cur[c] = on ? a.theta[row + ch] : 1.0;
-                sc[c] = on ? a.scale[row + ch] : 1.0;
+                const double cur = on ? a.theta[row + ch] : 1.0;
+                const double sc = on ? a.scale[row + ch] : 1.0;
                 double z;
                 if (a.tape_z != nullptr) {
                     z = on ? a.tape_z[row + ch] : 0.0;
@@ -497,7 +565,7 @@ __global__ void __launch_bounds__(256, MINB) sweep_kernel(const SweepArgs a) {
                     z = normal_from(rnd.x, rnd.y);
                     uu[c] = uniform_from(rnd.z, rnd.w);
                 }
-                prop[c] = __dadd_rn(cur[c], __dmul_rn(sc[c], z));      // numpy.random.normal(value, sd), :304-306
+                prop[c] = __dadd_rn(cur, __dmul_rn(sc, z));            // numpy.random.normal(value, sd), :304-306
                 const T pt = Obj::template local<T>(p, prop[c], a.obj_const, g);
 #pragma unroll
                 for (int k = 0; k < P; ++k) {
@@ -505,37 +573,42 @@ __global__ void __launch_bounds__(256, MINB) sweep_kernel(const SweepArgs a) {
                 }
             }
 
-            double llp[C];
-            group_loglik<Obj, C, T>(a, blk, tile, g, R, mb, parity, th, llp);
+            double acc[C];
+            group_loglik<Obj, C, T>(a, blk, tile, g, R, mb, parity, th, acc);
 
+            const bool new_aux = Obj::aux_depends_on(p);
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 const int ch = cbase + 32 * c;
                 const bool on = ch < a.n_chains;
+                typename Obj::Aux aux_prop = aux_cur[c];
+                if (new_aux) aux_prop = Obj::template aux<T>(R, th[c]);
+                const double llp = Obj::finish(acc[c], aux_prop);
+                const double cur = on ? a.theta[row + ch] : 1.0;
                 double lp_prop, lp_cur;
                 if (a.partial) {
                     const double mu = on ? a.hyper[((size_t)0 * P + p) * S + ch] : 0.0;
-                    const double sd = on ? a.hyper[((size_t)2 * P + p) * S + ch] : 1.0;
                     const double lsd = on ? a.hyper[((size_t)3 * P + p) * S + ch] : 0.0;
-                    lp_prop = norm_logpdf(prop[c], mu, sd, lsd);
-                    lp_cur = a.use_override ? (on ? a.lprior[row + ch] : 0.0) : norm_logpdf(cur[c], mu, sd, lsd);
+                    const double isd = on ? a.hyper[((size_t)4 * P + p) * S + ch] : 1.0;
+                    lp_prop = norm_logpdf_inv(prop[c], mu, isd, lsd);
+                    lp_cur = a.use_override ? (on ? a.lprior[row + ch] : 0.0) : norm_logpdf_inv(cur, mu, isd, lsd);
                 } else {
                     lp_prop = prior_logpdf(a.prior[p], prop[c]);
                     lp_cur = on ? a.lprior[row + ch] : 0.0;
                 }
                 // Parameter.step decision tree, :334-367
-                const double post_prop = lp_prop + llp[c];
+                const double post_prop = lp_prop + llp;
                 const double post_cur = lp_cur + llcur[c];
                 const double diff = post_prop - post_cur;
                 bool acc_own;
                 if (!isfinite(post_cur) && isfinite(post_prop)) acc_own = true;
-                else if (!isfinite(llp[c])) acc_own = false;
+                else if (!isfinite(llp)) acc_own = false;
                 else if (!isfinite(diff)) acc_own = false;
-                else acc_own = log(uu[c]) < diff;
+                else acc_own = log_u_less_than(uu[c], diff);
                 bool accept = acc_own;
                 if (on) {
                     if (a.tr_ll != nullptr) {
-                        a.tr_ll[row + ch] = llp[c];
+                        a.tr_ll[row + ch] = llp;
                         a.tr_lp[row + ch] = lp_prop;
                         a.tr_diff[row + ch] = diff;
                         a.tr_acc[row + ch] = acc_own ? 1 : 0;
@@ -545,7 +618,8 @@ __global__ void __launch_bounds__(256, MINB) sweep_kernel(const SweepArgs a) {
                 accept = accept && on;
                 if (accept) {                                        // :369-378, :608-610
                     a.theta[row + ch] = prop[c];
-                    llcur[c] = llp[c];
+                    llcur[c] = llp;
+                    aux_cur[c] = aux_prop;
                     if (!a.partial) a.lprior[row + ch] = lp_prop;
                 }
 #pragma unroll
@@ -558,6 +632,7 @@ __global__ void __launch_bounds__(256, MINB) sweep_kernel(const SweepArgs a) {
                     if (a.tune) {                                    // Parameter.tune, :385-437
                         const unsigned na = cnt & 0xFFFFu, nr = cnt >> 16;
                         if (na + nr) {
+                            const double sc = a.scale[row + ch];
                             const double rate = (double)na / (double)(na + nr);
                             double f = 1.0;
                             if (rate < 0.001) f = 0.1;
@@ -566,8 +641,8 @@ __global__ void __launch_bounds__(256, MINB) sweep_kernel(const SweepArgs a) {
                             else if (rate > 0.95) f = 10.0;
                             else if (rate > 0.75) f = 2.0;
                             else if (rate > 0.5) f = 1.1;
-                            double ns = __dmul_rn(sc[c], f);
-                            if (ns == 0.0) ns = sc[c];
+                            double ns = __dmul_rn(sc, f);
+                            if (ns == 0.0) ns = sc;
                             a.scale[row + ch] = ns;
                             cnt = 0;
                         }
@@ -581,7 +656,6 @@ __global__ void __launch_bounds__(256, MINB) sweep_kernel(const SweepArgs a) {
             const int ch = cbase + 32 * c;
             if (ch < a.n_chains) a.ll[(size_t)g * S + ch] = llcur[c];
         }
-        (void)nan_;
     }
 }
 
@@ -624,7 +698,7 @@ __global__ void __launch_bounds__(256) eval_kernel(const SweepArgs a) {
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const int ch = cbase + 32 * c;
-            if (ch < a.n_chains) a.out_ll[(size_t)g * S + ch] = out[c];
+            if (ch < a.n_chains) a.out_ll[(size_t)g * S + ch] = Obj::finish(out[c], Obj::template aux<T>(R, th[c]));
         }
     }
 }
@@ -743,6 +817,7 @@ __global__ void __launch_bounds__(32 * NS) hyper_kernel(const HyperArgs a) {
         a.hyper[((size_t)1 * a.P + p) * S + ch] = sigma2;
         a.hyper[((size_t)2 * a.P + p) * S + ch] = sd;
         a.hyper[((size_t)3 * a.P + p) * S + ch] = log(sd);
+        a.hyper[((size_t)4 * a.P + p) * S + ch] = 1.0 / sd;
     }
 }
 

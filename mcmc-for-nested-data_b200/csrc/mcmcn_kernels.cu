@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "mcmcn_device.cuh"
 #include "mcmcn_host.h"
@@ -193,6 +194,18 @@ int mcmcn_run(const mcmcn_model* m, const mcmcn_state* s, const mcmcn_run_args* 
     if (r->burn > 0) last_tune = ((long long)(r->burn - 1) / r->tune_interval) * r->tune_interval;
     int64_t row = r->store_row0;
 
+    // optional per-kernel timing: one event pair per launch, summed after the last launch
+    struct Stamp { cudaEvent_t e0, e1; int kind; };
+    std::vector<Stamp> stamps;
+    auto tic = [&](int kind) {
+        if (!r->timing) return;
+        Stamp s; s.kind = kind;
+        cudaEventCreate(&s.e0); cudaEventCreate(&s.e1);
+        cudaEventRecord(s.e0, stream);
+        stamps.push_back(s);
+    };
+    auto toc = [&]() { if (r->timing) cudaEventRecord(stamps.back().e1, stream); };
+
     for (int it = 0; it < r->n_iter; ++it) {
         const long long i = r->iter0 + it;
         a.iter = i;
@@ -208,7 +221,9 @@ int mcmcn_run(const mcmcn_model* m, const mcmcn_state* s, const mcmcn_run_args* 
         a.tr_diff = r->trace_diff ? r->trace_diff + it * per_iter : nullptr;
         a.tr_acc = r->trace_accept ? r->trace_accept + it * per_iter : nullptr;
         if (a.tr_ll && !(a.tr_lp && a.tr_diff && a.tr_acc)) { set_error("trace arrays go together"); return MCMCN_ERR_INVALID; }
+        tic(0);
         fn<<<g.grid, g.block, g.smem, stream>>>(a);
+        toc();
 
         if (partial) {
             HyperArgs h;
@@ -218,24 +233,39 @@ int mcmcn_run(const mcmcn_model* m, const mcmcn_state* s, const mcmcn_run_args* 
             h.tape_zmu = r->tape_zmu ? r->tape_zmu + it * per_iter_h : nullptr;
             h.tape_qsig = r->tape_qsig ? r->tape_qsig + it * per_iter_h : nullptr;
             const dim3 hg((unsigned)((s->n_chains + 31) / 32), (unsigned)m->n_params, 1);
+            tic(1);
             if (m->n_groups >= 64) hyper_kernel<8><<<hg, dim3(32, 8, 1), 0, stream>>>(h);
             else hyper_kernel<1><<<hg, dim3(32, 1, 1), 0, stream>>>(h);
+            toc();
         }
 
         if (r->store && i >= r->burn && (i % r->thin) == 0) {
             if (row >= r->store_rows) { set_error("sample store overflow at row %lld", (long long)row); return MCMCN_ERR_INVALID; }
             const dim3 sg((unsigned)((s->n_chains + 127) / 128), (unsigned)ncol, 1);
             if (ncol > 65535) { set_error("more than 65535 columns per row not supported yet"); return MCMCN_ERR_UNSUPPORTED; }
+            tic(2);
             if (r->store_dtype == 64)
                 snapshot_kernel<double><<<sg, 128, 0, stream>>>(m->n_params, m->n_groups, partial ? 1 : 0, s->n_chains, s->stride,
                                                                 s->theta, s->hyper, (double*)r->store + (size_t)row * ncol * S);
             else
                 snapshot_kernel<float><<<sg, 128, 0, stream>>>(m->n_params, m->n_groups, partial ? 1 : 0, s->n_chains, s->stride,
                                                                s->theta, s->hyper, (float*)r->store + (size_t)row * ncol * S);
+            toc();
             ++row;
         }
     }
     CK(cudaGetLastError());
+    if (r->timing && !stamps.empty()) {
+        CK(cudaEventSynchronize(stamps.back().e1));
+        for (Stamp& s : stamps) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, s.e0, s.e1);
+            r->timing[s.kind] += ms;
+            r->timing[3 + s.kind] += 1.0;
+            cudaEventDestroy(s.e0);
+            cudaEventDestroy(s.e1);
+        }
+    }
     return MCMCN_OK;
 }
 

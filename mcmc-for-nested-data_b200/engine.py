@@ -192,7 +192,7 @@ class Engine(object):
         self.counts = torch.zeros((P, G, S), dtype=torch.int32, device=dev)
         self.ll = torch.full((G, S), float("nan"), dtype=f64, device=dev)    # :265
         self.lprior = torch.zeros((P, G, S), dtype=f64, device=dev)
-        self.hyper = torch.zeros((4, P, S), dtype=f64, device=dev) if self.partial else None
+        self.hyper = torch.zeros((5, P, S), dtype=f64, device=dev) if self.partial else None
         self.lpriorStale = False
         st = nat.State()
         st.n_chains = self.nChains
@@ -219,7 +219,8 @@ class Engine(object):
         with numpy.errstate(all="ignore"):
             sd = numpy.sqrt(sigma2)
             lsd = numpy.log(sd)
-        self._up(self.hyper, numpy.stack([mu, sigma2, sd, lsd]))
+            isd = 1.0 / sd
+        self._up(self.hyper, numpy.stack([mu, sigma2, sd, lsd, isd]))
 
     def setState(self, theta, ll, lprior=None, mu=None, sigma2=None, scale=None, counts=None):
         """Host arrays with the chain as LAST axis: theta/lprior/scale [P][G][nC], ll [G][nC]."""
@@ -319,7 +320,7 @@ class Engine(object):
 
     # ------------------------------------------------------------------ run loop
     def run(self, iter0, nIter, burn, thin, store=None, tape=None, trace=False,
-            tuneInterval=100, useLpriorOverride=None):
+            tuneInterval=100, useLpriorOverride=None, timing=None):
         """Advance every chain by nIter iterations (Sampler._loop, :862-896)."""
         P, G, S = self.P, self.G, self.S
         a = nat.RunArgs()
@@ -349,6 +350,8 @@ class Engine(object):
         if useLpriorOverride is None:
             useLpriorOverride = self.partial and self.lpriorStale and iter0 == 0
         a.use_lprior_override = 1 if useLpriorOverride else 0
+        if timing is not None:      # numpy float64[8], accumulated into (per-kernel ms and launch counts)
+            a.timing = timing.ctypes.data_as(ctypes.c_void_p)
         nat.call("mcmcn_run", ctypes.byref(self.model), ctypes.byref(self.state), ctypes.byref(a), self.stream)
         if iter0 == 0 and nIter > 0:
             self.lpriorStale = False

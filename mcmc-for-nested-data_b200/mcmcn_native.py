@@ -71,7 +71,8 @@ class RunArgs(ctypes.Structure):
                 ("trace_accept", c_void_p),
                 ("store", c_void_p), ("store_dtype", ctypes.c_int32),
                 ("use_lprior_override", ctypes.c_int32),
-                ("store_row0", ctypes.c_int64), ("store_rows", ctypes.c_int64)]
+                ("store_row0", ctypes.c_int64), ("store_rows", ctypes.c_int64),
+                ("timing", c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/mcmcn.h declares

@@ -117,14 +117,15 @@ class Objective(object):
             rows = slice(start, start + r)
             if self.kind == nat.OBJ_LINEAR_REGRESSION:
                 # centre the group on its least-squares fit (FP32 conditioning, see LinReg in
-                # csrc/mcmcn_device.cuh): store e = y - X.bbar, keep bbar in FP64
+                # csrc/mcmcn_device.cuh): store ne = X.bbar - y, keep bbar in FP64
                 Xg, yg = self.X[rows], self.y[rows]
                 bbar[g] = numpy.linalg.lstsq(Xg, yg, rcond=None)[0] if r > 0 else 0.0
                 xs = numpy.zeros((q * 4, KP), dtype=dt)
                 xs[:r, :K] = Xg
                 ys = numpy.zeros(q * 4, dtype=dt)
-                ys[:r] = yg - Xg @ bbar[g]
-                blk[:, :4 * KP] = xs.reshape(q, 4 * KP)
+                ys[:r] = Xg @ bbar[g] - yg                      # ne = x.bbar - y
+                # quad layout [KP][4 obs] (coefficient-major), then [4] ne
+                blk[:, :4 * KP] = xs.reshape(q, 4, KP).transpose(0, 2, 1).reshape(q, 4 * KP)
                 blk[:, 4 * KP:] = ys.reshape(q, 4)
             elif self.kind == nat.OBJ_BERNOULLI_LOGIT:
                 xs = numpy.zeros(q * 4, dtype=dt)
