@@ -81,25 +81,26 @@ __device__ __forceinline__ uint4 philox_draw(long long chain_id, unsigned long l
     const uint2 key = make_uint2((unsigned)chain_id ^ (unsigned)(seed >> 32) * 0x9E3779B1u, (unsigned)seed ^ (unsigned)(chain_id >> 32));
     return philox4x32_10(ctr, key);
 }
-// standard normal from two 32-bit words (Box-Muller at fp32 resolution on the MUFU unit:
-// lg2, rsq-based sqrt, cos; symmetric about 0, |z| <= 5.8)
+// standard normal from two 32-bit words (Box-Muller at fp32 resolution, branch-free on the MUFU
+// unit: lg2, sqrt, cos; symmetric about 0, |z| <= 5.8)
 __device__ __forceinline__ double normal_from(unsigned a, unsigned b) {
     const float u1 = (float)((a >> 8) + 1u) * 5.9604644775390625e-8f;   // (0, 1]
     const float u2 = (float)(b >> 8) * 5.9604644775390625e-8f;          // [0, 1)
-    const float r = sqrtf(-2.0f * __logf(u1));
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));
     return (double)(r * __cosf(6.283185307179586f * u2));
 }
-// log(u) < diff, decided in FP32 when the margin allows and in FP64 otherwise.  __logf is
-// accurate to 2^-21.41 absolute on [0.5, 2] and 3 ulp elsewhere; (float)u adds 6e-8 relative,
-// so |__logf((float)u) - log(u)| < 1e-6 * (1 + |log u|) with a wide margin.
-__device__ __forceinline__ bool log_u_less_than(double u, double diff) {
+// log(u) < diff decided in FP32 when the margin allows: returns +1 (true), -1 (false) or 0
+// (too close to call: the caller falls back to the FP64 logarithm, about once per 10^5
+// decisions).  __logf is accurate to 2^-21.41 absolute on [0.5, 2] and 3 ulp elsewhere and
+// (float)u adds 6e-8 relative, so |__logf((float)u) - log(u)| < 1e-6 * (1 + |log u|) with a
+// wide margin; rounding diff to FP32 moves it by at most 6e-8 relative.
+__device__ __forceinline__ int log_u_vs_diff_fast(double u, double diff) {
     const float lu = __logf((float)u);
     const float tol = 1e-6f * (1.0f + fabsf(lu));
-    const float d = (float)diff;                      // rounding of diff: relative 6e-8, inside tol for |diff| ~ |lu|
+    const float d = (float)diff;
     const float dtol = 1.2e-7f * fabsf(d);
-    if (d - dtol > lu + tol) return true;
-    if (d + dtol < lu - tol) return false;
-    return log(u) < diff;
+    return (d - dtol > lu + tol) ? 1 : ((d + dtol < lu - tol) ? -1 : 0);
 }
 // uniform in [0,1) with 53 random bits, numpy's recipe (legacy random_sample)
 __device__ __forceinline__ double uniform_from(unsigned a, unsigned b) {
@@ -114,12 +115,18 @@ __device__ __forceinline__ double norm_logpdf(double x, double loc, double scale
     return (!(scale > 0.0) || y != y) ? __longlong_as_double(0x7ff8000000000000LL) : r;
 }
 // same with the reciprocal of the scale precomputed (group-level prior of partial pooling: two
-// evaluations per decision; differs from the quotient form by at most 1 ulp of y)
+// evaluations per decision; differs from the quotient form by at most 1 ulp of y); branch-free
 __device__ __forceinline__ double norm_logpdf_inv(double x, double loc, double inv_scale, double log_scale) {
     const double y = __dmul_rn(__dsub_rn(x, loc), inv_scale);
     const double r = __dsub_rn(__dsub_rn(-0.5 * __dmul_rn(y, y), MCMCN_LOG_SQRT_2PI), log_scale);
-    return (!(inv_scale > 0.0) || !(inv_scale < __longlong_as_double(0x7ff0000000000000LL)) || y != y)
-               ? norm_logpdf(x, loc, 1.0 / inv_scale, log_scale) : r;
+    const bool ok = inv_scale > 0.0 && inv_scale < __longlong_as_double(0x7ff0000000000000LL) && y == y;
+    return ok ? r : __longlong_as_double(0x7ff8000000000000LL);
+}
+__device__ __forceinline__ bool finite64(double v) {
+    return (__double2hiint(v) & 0x7ff00000) != 0x7ff00000;
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
 __device__ __forceinline__ double prior_logpdf(const mcmcn_prior& pr, double x) {
     const double ninf = __longlong_as_double(0xfff0000000000000LL);
@@ -155,11 +162,14 @@ __device__ __forceinline__ double prior_logpdf(const mcmcn_prior& pr, double x) 
 }
 
 // ---------------------------------------------------------------- objective policies
-// A policy restates one reference-style objective as a device function over a
-// group's packed block in shared memory.  `accumulate` adds the block's
-// contribution for C chains at once (th[c][p] = parameter p of chain slot c),
-// `finish` turns the accumulator into the group log-likelihood, `pointwise`
-// gives one observation's log-likelihood (saveLogLikelihood path).
+// A policy restates one reference-style objective as a device function over a group's packed
+// block in shared memory.
+//   Work<C,T>     the C chains' parameters of the current group in the form the hot loop wants
+//   local         FP64 parameter value -> working value
+//   accumulate    adds the block's contribution for the C chains at once
+//   Aux / aux     per-chain terms of the group log-likelihood outside the observation loop
+//   finish        accumulator + Aux -> group log-likelihood
+//   pointwise     one observation's log-likelihood (saveLogLikelihood path)
 
 template <typename T> struct Vec4 {};
 template <> struct Vec4<float> {
@@ -178,6 +188,27 @@ template <> struct Vec4<double> {
 __device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
 __device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
 
+// Parameters as a plain register array; `p` is a run-time index, `c` is always a literal after
+// unrolling, so every access below is a chain of selects, never local memory.
+template <int P, int C, typename T>
+struct PlainWork {
+    T th[C][P];
+    __device__ __forceinline__ void set(int c, int p, T v) {
+#pragma unroll
+        for (int k = 0; k < P; ++k) if (k == p) th[c][k] = v;
+    }
+    __device__ __forceinline__ T get(int c, int p) const {
+        T r = th[c][0];
+#pragma unroll
+        for (int k = 1; k < P; ++k) if (k == p) r = th[c][k];
+        return r;
+    }
+    __device__ __forceinline__ void row(int c, T (&out)[P]) const {
+#pragma unroll
+        for (int k = 0; k < P; ++k) out[k] = th[c][k];
+    }
+};
+
 // Packed FP32x2 FMA (PTX fma.rn.f32x2, SASS FFMA2; new on sm_100).  A 64-bit operand is an
 // aligned even/odd register pair, so an FFMA2 with one operand served from the reuse cache
 // reads exactly one register per bank per FMA: measured 116.7 FMA lanes/clk/SM on B200 whatever
@@ -194,6 +225,11 @@ __device__ __forceinline__ f32x2 pack2(float lo, float hi) {
     f32x2 d;
     asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
     return d;
+}
+__device__ __forceinline__ float lo2(f32x2 v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return lo;
 }
 __device__ __forceinline__ float sum2(f32x2 v) {
     float lo, hi;
@@ -220,28 +256,51 @@ struct LinReg {
     static constexpr int HDR = 0;
     static constexpr int OBS_PER_UNIT = 4;
 
-    // parameter p of group g as the kernel's working value
     template <typename T>
     __device__ static __forceinline__ T local(int p, double v, const double* cst, int g) {
         return (T)(p < K ? __dsub_rn(v, cst[(size_t)g * K + p]) : v);
     }
 
-    // FP32 hot loop: sum of squared residuals of C chains over the block, two observations per FFMA2.
+    // FP64: plain array.  FP32: every coefficient duplicated into an FFMA2 operand pair.
+    template <int C, typename T, int Dummy = 0>
+    struct Work : PlainWork<P, C, T> {
+        __device__ __forceinline__ double sigma(int c) const { return (double)this->th[c][K]; }
+    };
+    template <int C, int Dummy>
+    struct Work<C, float, Dummy> {
+        f32x2 b2[C][K];
+        float sg[C];
+        __device__ __forceinline__ void set(int c, int p, float v) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) if (k == p) b2[c][k] = pack2(v, v);
+            if (p == K) sg[c] = v;
+        }
+        __device__ __forceinline__ float get(int c, int p) const {
+            float r = sg[c];
+#pragma unroll
+            for (int k = 0; k < K; ++k) if (k == p) r = lo2(b2[c][k]);
+            return r;
+        }
+        __device__ __forceinline__ void row(int c, float (&out)[P]) const {
+#pragma unroll
+            for (int k = 0; k < K; ++k) out[k] = lo2(b2[c][k]);
+            out[K] = sg[c];
+        }
+        __device__ __forceinline__ double sigma(int c) const { return (double)sg[c]; }
+    };
+
+    // FP32 hot loop: sum of squared residuals of C chains over the block, two observations per
+    // FFMA2, FP32 partial sums folded into FP64 every 16 observations.
     template <int C>
     __device__ static __forceinline__ void accumulate(const float* __restrict__ blk, int nobs, const double*,
-                                                      const float (&th)[C][P], double (&acc)[C]) {
-        f32x2 th2[C][K];
-#pragma unroll
-        for (int c = 0; c < C; ++c)
-#pragma unroll
-            for (int k = 0; k < K; ++k) th2[c][k] = pack2(th[c][k], th[c][k]);
+                                                      const Work<C, float>& w, double (&acc)[C]) {
         const int nq = (nobs + 3) >> 2;
-        for (int q0 = 0; q0 < nq; q0 += 2) {
+        for (int q0 = 0; q0 < nq; q0 += 4) {
             f32x2 s2[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) s2[c] = 0ull;
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < 4; ++u) {
                 if (q0 + u < nq) {
                     const float* xq = blk + (size_t)(q0 + u) * UNIT;
                     const ulonglong2 ne = *reinterpret_cast<const ulonglong2*>(xq + 4 * KP);
@@ -250,9 +309,9 @@ struct LinReg {
                     for (int k = 0; k < K; ++k) {
                         const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(xq + 4 * k);
 #pragma unroll
-                        for (int c = 0; c < C; ++c) r[c][0] = ffma2(x.x, th2[c][k], k == 0 ? ne.x : r[c][0]);
+                        for (int c = 0; c < C; ++c) r[c][0] = ffma2(x.x, w.b2[c][k], k == 0 ? ne.x : r[c][0]);
 #pragma unroll
-                        for (int c = 0; c < C; ++c) r[c][1] = ffma2(x.y, th2[c][k], k == 0 ? ne.y : r[c][1]);
+                        for (int c = 0; c < C; ++c) r[c][1] = ffma2(x.y, w.b2[c][k], k == 0 ? ne.y : r[c][1]);
                     }
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
@@ -262,13 +321,13 @@ struct LinReg {
                 }
             }
 #pragma unroll
-            for (int c = 0; c < C; ++c) acc[c] += (double)sum2(s2[c]);   // FP64 fold every 8 observations
+            for (int c = 0; c < C; ++c) acc[c] += (double)sum2(s2[c]);
         }
     }
     // FP64 path (replay verification): same layout, scalar FMAs.
     template <int C>
     __device__ static __forceinline__ void accumulate(const double* __restrict__ blk, int nobs, const double*,
-                                                      const double (&th)[C][P], double (&acc)[C]) {
+                                                      const Work<C, double>& w, double (&acc)[C]) {
         const int nq = (nobs + 3) >> 2;
         for (int q = 0; q < nq; ++q) {
             const double* xq = blk + (size_t)q * UNIT;
@@ -278,7 +337,7 @@ struct LinReg {
                 for (int c = 0; c < C; ++c) {
                     double r = xq[4 * KP + j];
 #pragma unroll
-                    for (int k = 0; k < K; ++k) r = fma(xq[4 * k + j], th[c][k], r);
+                    for (int k = 0; k < K; ++k) r = fma(xq[4 * k + j], w.th[c][k], r);
                     acc[c] = fma(r, r, acc[c]);
                 }
             }
@@ -286,9 +345,9 @@ struct LinReg {
     }
     // Per-chain terms that only change when sigma does: -1/(2 sigma^2) and R*(log sigma + log sqrt(2 pi)).
     struct Aux { double mhalf_inv2, rlog; };
-    template <typename T>
-    __device__ static __forceinline__ Aux aux(int R, const T (&th)[P]) {
-        const double sg = (double)th[K];
+    template <int C, typename T>
+    __device__ static __forceinline__ Aux aux(int R, const Work<C, T>& w, int c) {
+        const double sg = w.sigma(c);
         Aux a;
         if (!(sg > 0.0)) {                                    // scipy: scale <= 0 -> nan
             a.mhalf_inv2 = a.rlog = __longlong_as_double(0x7ff8000000000000LL);
@@ -333,10 +392,12 @@ struct Logit {
 
     template <typename T>
     __device__ static __forceinline__ T local(int, double v, const double*, int) { return (T)v; }
+    template <int C, typename T>
+    struct Work : PlainWork<P, C, T> {};
 
     template <int C, typename T>
     __device__ static __forceinline__ void accumulate(const T* __restrict__ blk, int nobs, const double*,
-                                                      const T (&th)[C][P], double (&acc)[C]) {
+                                                      const Work<C, T>& w, double (&acc)[C]) {
         const int nq = nobs >> 2;
         for (int q = 0; q < nq; ++q) {
             T x4[4], y4[4];
@@ -349,7 +410,7 @@ struct Logit {
             for (int j = 0; j < 4; ++j) {
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    const T eta = fma_t(th[c][1], x4[j], th[c][0]);
+                    const T eta = fma_t(w.th[c][1], x4[j], w.th[c][0]);
                     s[c] += fma_t(y4[j], eta, -softplus_t(eta));
                 }
             }
@@ -361,14 +422,14 @@ struct Logit {
         for (int j = 0; j < rem; ++j) {
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                const T eta = fma_t(th[c][1], xq[j], th[c][0]);
+                const T eta = fma_t(w.th[c][1], xq[j], w.th[c][0]);
                 acc[c] += (double)fma_t(xq[4 + j], eta, -softplus_t(eta));
             }
         }
     }
     struct Aux {};
-    template <typename T>
-    __device__ static __forceinline__ Aux aux(int, const T (&)[P]) { return Aux(); }
+    template <int C, typename T>
+    __device__ static __forceinline__ Aux aux(int, const Work<C, T>&, int) { return Aux(); }
     __device__ static __forceinline__ bool aux_depends_on(int) { return false; }
     __device__ static __forceinline__ double finish(double acc, const Aux&) { return acc; }
     template <typename T>
@@ -395,6 +456,8 @@ struct GaussDist {
 
     template <typename T>
     __device__ static __forceinline__ T local(int, double v, const double*, int) { return (T)v; }
+    template <int C, typename T>
+    struct Work : PlainWork<P, C, T> {};
 
     template <typename T>
     __device__ static __forceinline__ T row(const T* __restrict__ rec, const double* cst, const T (&th)[P]) {
@@ -408,16 +471,16 @@ struct GaussDist {
     }
     template <int C, typename T>
     __device__ static __forceinline__ void accumulate(const T* __restrict__ blk, int nobs, const double* cst,
-                                                      const T (&th)[C][P], double (&acc)[C]) {
+                                                      const Work<C, T>& w, double (&acc)[C]) {
         for (int i = 0; i < nobs; ++i) {   // one evaluation per observation, summed in order (:631-633)
             const T* rec = blk + (size_t)(i >> 2) * UNIT + (i & 3) * PP;
 #pragma unroll
-            for (int c = 0; c < C; ++c) acc[c] = __dadd_rn(acc[c], (double)row<T>(rec, cst, th[c]));
+            for (int c = 0; c < C; ++c) acc[c] = __dadd_rn(acc[c], (double)row<T>(rec, cst, w.th[c]));
         }
     }
     struct Aux {};
-    template <typename T>
-    __device__ static __forceinline__ Aux aux(int, const T (&)[P]) { return Aux(); }
+    template <int C, typename T>
+    __device__ static __forceinline__ Aux aux(int, const Work<C, T>&, int) { return Aux(); }
     __device__ static __forceinline__ bool aux_depends_on(int) { return false; }
     __device__ static __forceinline__ double finish(double acc, const Aux&) { return acc; }
     template <typename T>
@@ -463,6 +526,14 @@ struct SweepArgs {
     double* out_ll;               // [G][S]
 };
 
+// Compile-time specialisation of the step kernel.  F < 0: everything decided at run time (the
+// general kernel: replay tapes, traces, groups streamed through the tile).  F >= 0: the
+// production variants -- no tape, no trace, every task fits the tile -- with the pooling mode
+// and the burn-in bookkeeping folded at compile time, which removes a third of the
+// per-decision instructions and most of the kernel's code size.
+#define MCMCN_F_PARTIAL 1
+#define MCMCN_F_COUNT 2
+
 // Stage `elems` elements starting at `src` into the tile and wait for them.
 // All threads of the CTA call this; thread 0 issues the TMA bulk copy.
 template <typename T>
@@ -480,15 +551,15 @@ __device__ __forceinline__ void stage_tile(T* tile, const T* src, long long elem
 
 // Group accumulators (Obj::finish turns them into log-likelihoods) for C chains; the group's
 // block is either resident in the tile (blk != NULL) or streamed through it in chunks.
-template <class Obj, int C, typename T>
+template <class Obj, int C, typename T, bool STREAM>
 __device__ __forceinline__ void group_loglik(const SweepArgs& a, const T* blk, T* tile, int g, int R, unsigned mb,
-                                             unsigned& parity, const T (&th)[C][Obj::P], double (&acc)[C]) {
+                                             unsigned& parity, const typename Obj::template Work<C, T>& w,
+                                             double (&acc)[C]) {
 #pragma unroll
     for (int c = 0; c < C; ++c) acc[c] = 0.0;
-    if (blk != nullptr) {
-        Obj::template accumulate<C>(blk + Obj::HDR, R, a.obj_const, th, acc);
+    if (!STREAM || blk != nullptr) {
+        Obj::template accumulate<C>(blk + Obj::HDR, R, a.obj_const, w, acc);
     } else {
-        // streaming: header stays out of the tile (objectives with a header always fit)
         const T* src = reinterpret_cast<const T*>(a.data) + a.group_off[g] + Obj::HDR;
         const int unit = Obj::UNIT > 0 ? Obj::UNIT : 1;
         const int chunk_obs = (a.tile_cap_elems / unit) * Obj::OBS_PER_UNIT;
@@ -496,7 +567,7 @@ __device__ __forceinline__ void group_loglik(const SweepArgs& a, const T* blk, T
             const int n = min(chunk_obs, R - o);
             const long long elems = (long long)((n + Obj::OBS_PER_UNIT - 1) / Obj::OBS_PER_UNIT) * Obj::UNIT;
             stage_tile<T>(tile, src + (long long)(o / Obj::OBS_PER_UNIT) * Obj::UNIT, elems, mb, parity, true);
-            Obj::template accumulate<C>(tile, n, a.obj_const, th, acc);
+            Obj::template accumulate<C>(tile, n, a.obj_const, w, acc);
         }
     }
 }
@@ -504,9 +575,17 @@ __device__ __forceinline__ void group_loglik(const SweepArgs& a, const T* blk, T
 // ---------------------------------------------------------------- the step kernel
 // grid = (tasks, chain blocks); block = NW warps; one warp = 32*C chains of one group at a time.
 // MINB = minimum resident CTAs per SM the register allocation must allow (2 -> at most 128 registers).
-template <class Obj, int C, typename T, int MINB>
+template <class Obj, int C, typename T, int MINB, int F>
 __global__ void __launch_bounds__(256, MINB) sweep_kernel(const SweepArgs a) {
     constexpr int P = Obj::P;
+    constexpr bool GENERAL = F < 0;
+    const bool partial = GENERAL ? (a.partial != 0) : ((F & MCMCN_F_PARTIAL) != 0);
+    const bool count = GENERAL ? (a.count != 0) : ((F & MCMCN_F_COUNT) != 0);
+    const bool replay = GENERAL && a.tape_z != nullptr;
+    const bool trace = GENERAL && a.tr_ll != nullptr;
+    const bool forced = GENERAL && a.tape_acc != nullptr;
+    const bool override_lp = GENERAL && a.use_override != 0;
+
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* tile = reinterpret_cast<T*>(smem_raw);
     __shared__ unsigned long long mbar_storage;
@@ -515,7 +594,7 @@ __global__ void __launch_bounds__(256, MINB) sweep_kernel(const SweepArgs a) {
     const int task = blockIdx.x;
     const int g0 = a.task_group0[task], g1 = a.task_group0[task + 1];
     const long long e0 = a.group_off[g0], e1 = a.group_off[g1];
-    const bool fits = (e1 - e0) <= (long long)a.tile_cap_elems;
+    const bool fits = !GENERAL || (e1 - e0) <= (long long)a.tile_cap_elems;
     if (threadIdx.x == 0) mbar_init(mb, 1);
     __syncthreads();
     unsigned parity = 0;
@@ -524,115 +603,162 @@ __global__ void __launch_bounds__(256, MINB) sweep_kernel(const SweepArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int cbase = (blockIdx.y * nw + warp) * (32 * C) + lane;
     const size_t S = (size_t)a.S;
-    const double nan_ = __longlong_as_double(0x7ff8000000000000LL);
+    // lanes past the last chain redo the last chain's work and store nothing
+    int chl[C];
+    bool on[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        on[c] = cbase + 32 * c < a.n_chains;
+        chl[c] = min(cbase + 32 * c, a.n_chains - 1);
+    }
 
     for (int g = g0; g < g1; ++g) {
         const int R = a.group_nobs[g];
         const T* blk = fits ? tile + (a.group_off[g] - e0) : nullptr;
 
-        T th[C][P];
+        typename Obj::template Work<C, T> w;
         double llcur[C];
         typename Obj::Aux aux_cur[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            const int ch = cbase + 32 * c;
-            const bool on = ch < a.n_chains;
 #pragma unroll
             for (int p = 0; p < P; ++p)
-                th[c][p] = on ? Obj::template local<T>(p, a.theta[((size_t)p * a.G + g) * S + ch], a.obj_const, g) : (T)1;
-            llcur[c] = on ? a.ll[(size_t)g * S + ch] : 0.0;
-            aux_cur[c] = Obj::template aux<T>(R, th[c]);
+                w.set(c, p, Obj::template local<T>(p, a.theta[((size_t)p * a.G + g) * S + chl[c]], a.obj_const, g));
+            llcur[c] = a.ll[(size_t)g * S + chl[c]];
+            aux_cur[c] = Obj::template aux<C, T>(R, w, c);
         }
 
 #pragma unroll 1
         for (int p = 0; p < P; ++p) {
+            // Written stage by stage over the C chains with selects instead of branches, so that
+            // the C independent dependency chains interleave in one basic block.
             const size_t row = ((size_t)p * a.G + g) * S;
             double prop[C], uu[C];
             T old[C];
+            {
+                double cur[C], sc[C], z[C];
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const int ch = cbase + 32 * c;
-                const bool on = ch < a.n_chains;
-                const double cur = on ? a.theta[row + ch] : 1.0;
-                const double sc = on ? a.scale[row + ch] : 1.0;
-                double z;
-                if (a.tape_z != nullptr) {
-                    z = on ? a.tape_z[row + ch] : 0.0;
-                    uu[c] = on ? a.tape_u[row + ch] : 0.5;
-                } else {
-                    const uint4 rnd = philox_draw(a.chain_id0 + ch, a.seed, a.iter, MCMCN_STREAM_SWEEP,
-                                                  (unsigned)(p * a.G + g), 0u);
-                    z = normal_from(rnd.x, rnd.y);
-                    uu[c] = uniform_from(rnd.z, rnd.w);
+                for (int c = 0; c < C; ++c) {
+                    cur[c] = a.theta[row + chl[c]];
+                    sc[c] = a.scale[row + chl[c]];
                 }
-                prop[c] = __dadd_rn(cur, __dmul_rn(sc, z));            // numpy.random.normal(value, sd), :304-306
-                const T pt = Obj::template local<T>(p, prop[c], a.obj_const, g);
+                if (p + 1 < P) {                                       // next sweep's state into L1 meanwhile
 #pragma unroll
-                for (int k = 0; k < P; ++k) {
-                    if (k == p) { old[c] = th[c][k]; th[c][k] = pt; }
+                    for (int c = 0; c < C; ++c) {
+                        prefetch_l1(a.theta + row + (size_t)a.G * S + chl[c]);
+                        prefetch_l1(a.scale + row + (size_t)a.G * S + chl[c]);
+                    }
+                }
+                if (replay) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        z[c] = a.tape_z[row + chl[c]];
+                        uu[c] = a.tape_u[row + chl[c]];
+                    }
+                } else {
+                    uint4 rnd[C];
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+                        rnd[c] = philox_draw(a.chain_id0 + chl[c], a.seed, a.iter, MCMCN_STREAM_SWEEP,
+                                             (unsigned)(p * a.G + g), 0u);
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        z[c] = normal_from(rnd[c].x, rnd[c].y);
+                        uu[c] = uniform_from(rnd[c].z, rnd[c].w);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    prop[c] = __dadd_rn(cur[c], __dmul_rn(sc[c], z[c]));   // numpy.random.normal(value, sd), :304-306
+                    old[c] = w.get(c, p);
+                    w.set(c, p, Obj::template local<T>(p, prop[c], a.obj_const, g));
                 }
             }
 
             double acc[C];
-            group_loglik<Obj, C, T>(a, blk, tile, g, R, mb, parity, th, acc);
+            group_loglik<Obj, C, T, GENERAL>(a, blk, tile, g, R, mb, parity, w, acc);
 
-            const bool new_aux = Obj::aux_depends_on(p);
+            typename Obj::Aux aux_prop[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) aux_prop[c] = aux_cur[c];
+            if (Obj::aux_depends_on(p)) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) aux_prop[c] = Obj::template aux<C, T>(R, w, c);
+            }
+            double llp[C], lp_prop[C], lp_cur[C];
+            if (partial) {
+                double mu[C], lsd[C], isd[C], cur[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    mu[c] = a.hyper[((size_t)0 * P + p) * S + chl[c]];
+                    lsd[c] = a.hyper[((size_t)3 * P + p) * S + chl[c]];
+                    isd[c] = a.hyper[((size_t)4 * P + p) * S + chl[c]];
+                    cur[c] = override_lp ? a.lprior[row + chl[c]] : a.theta[row + chl[c]];
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    lp_prop[c] = norm_logpdf_inv(prop[c], mu[c], isd[c], lsd[c]);
+                    lp_cur[c] = override_lp ? cur[c] : norm_logpdf_inv(cur[c], mu[c], isd[c], lsd[c]);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    lp_prop[c] = prior_logpdf(a.prior[p], prop[c]);
+                    lp_cur[c] = a.lprior[row + chl[c]];
+                }
+            }
+            // Parameter.step decision tree, :334-367
+            double diff[C];
+            bool acc_own[C];
+            bool exact_any = false;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                const int ch = cbase + 32 * c;
-                const bool on = ch < a.n_chains;
-                typename Obj::Aux aux_prop = aux_cur[c];
-                if (new_aux) aux_prop = Obj::template aux<T>(R, th[c]);
-                const double llp = Obj::finish(acc[c], aux_prop);
-                const double cur = on ? a.theta[row + ch] : 1.0;
-                double lp_prop, lp_cur;
-                if (a.partial) {
-                    const double mu = on ? a.hyper[((size_t)0 * P + p) * S + ch] : 0.0;
-                    const double lsd = on ? a.hyper[((size_t)3 * P + p) * S + ch] : 0.0;
-                    const double isd = on ? a.hyper[((size_t)4 * P + p) * S + ch] : 1.0;
-                    lp_prop = norm_logpdf_inv(prop[c], mu, isd, lsd);
-                    lp_cur = a.use_override ? (on ? a.lprior[row + ch] : 0.0) : norm_logpdf_inv(cur, mu, isd, lsd);
-                } else {
-                    lp_prop = prior_logpdf(a.prior[p], prop[c]);
-                    lp_cur = on ? a.lprior[row + ch] : 0.0;
-                }
-                // Parameter.step decision tree, :334-367
-                const double post_prop = lp_prop + llp;
-                const double post_cur = lp_cur + llcur[c];
-                const double diff = post_prop - post_cur;
-                bool acc_own;
-                if (!isfinite(post_cur) && isfinite(post_prop)) acc_own = true;
-                else if (!isfinite(llp)) acc_own = false;
-                else if (!isfinite(diff)) acc_own = false;
-                else acc_own = log_u_less_than(uu[c], diff);
-                bool accept = acc_own;
-                if (on) {
-                    if (a.tr_ll != nullptr) {
-                        a.tr_ll[row + ch] = llp;
-                        a.tr_lp[row + ch] = lp_prop;
-                        a.tr_diff[row + ch] = diff;
-                        a.tr_acc[row + ch] = acc_own ? 1 : 0;
-                    }
-                    if (a.tape_acc != nullptr) accept = a.tape_acc[row + ch] != 0;
-                }
-                accept = accept && on;
-                if (accept) {                                        // :369-378, :608-610
-                    a.theta[row + ch] = prop[c];
-                    llcur[c] = llp;
-                    aux_cur[c] = aux_prop;
-                    if (!a.partial) a.lprior[row + ch] = lp_prop;
-                }
+                llp[c] = Obj::finish(acc[c], aux_prop[c]);
+                const double post_prop = lp_prop[c] + llp[c];
+                const double post_cur = lp_cur[c] + llcur[c];
+                diff[c] = post_prop - post_cur;
+                const bool b1 = !finite64(post_cur) && finite64(post_prop);
+                const bool test = finite64(llp[c]) && finite64(diff[c]);       // branches 4/5 draw the uniform
+                const int fast = log_u_vs_diff_fast(uu[c], diff[c]);
+                acc_own[c] = b1 || (test && fast > 0);
+                exact_any = exact_any || (!b1 && test && fast == 0);
+            }
+            if (exact_any) {                                           // rare: within 1e-6 of the threshold
 #pragma unroll
-                for (int k = 0; k < P; ++k) {
-                    if (k == p && !accept) th[c][k] = old[c];
+                for (int c = 0; c < C; ++c) {
+                    const double post_cur = lp_cur[c] + llcur[c];
+                    const bool b1 = !finite64(post_cur) && finite64(lp_prop[c] + llp[c]);
+                    if (!b1 && finite64(llp[c]) && finite64(diff[c]) && log_u_vs_diff_fast(uu[c], diff[c]) == 0)
+                        acc_own[c] = log(uu[c]) < diff[c];
                 }
-                if (a.count && on) {
-                    unsigned cnt = a.counts[row + ch];
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const size_t at = row + chl[c];
+                bool accept = acc_own[c];
+                if (GENERAL) {
+                    if (trace && on[c]) {
+                        a.tr_ll[at] = llp[c];
+                        a.tr_lp[at] = lp_prop[c];
+                        a.tr_diff[at] = diff[c];
+                        a.tr_acc[at] = acc_own[c] ? 1 : 0;
+                    }
+                    if (forced) accept = a.tape_acc[at] != 0;
+                }
+                if (accept && on[c]) {                               // :369-378, :608-610
+                    a.theta[at] = prop[c];
+                    if (!partial) a.lprior[at] = lp_prop[c];
+                }
+                llcur[c] = accept ? llp[c] : llcur[c];
+                aux_cur[c] = accept ? aux_prop[c] : aux_cur[c];
+                if (!accept) w.set(c, p, old[c]);
+                if (count && on[c]) {
+                    unsigned cnt = a.counts[at];
                     cnt += accept ? 1u : 0x10000u;
                     if (a.tune) {                                    // Parameter.tune, :385-437
                         const unsigned na = cnt & 0xFFFFu, nr = cnt >> 16;
                         if (na + nr) {
-                            const double sc = a.scale[row + ch];
+                            const double sc = a.scale[at];
                             const double rate = (double)na / (double)(na + nr);
                             double f = 1.0;
                             if (rate < 0.001) f = 0.1;
@@ -643,19 +769,17 @@ __global__ void __launch_bounds__(256, MINB) sweep_kernel(const SweepArgs a) {
                             else if (rate > 0.5) f = 1.1;
                             double ns = __dmul_rn(sc, f);
                             if (ns == 0.0) ns = sc;
-                            a.scale[row + ch] = ns;
+                            a.scale[at] = ns;
                             cnt = 0;
                         }
                     }
-                    a.counts[row + ch] = cnt;
+                    a.counts[at] = cnt;
                 }
             }
         }
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            const int ch = cbase + 32 * c;
-            if (ch < a.n_chains) a.ll[(size_t)g * S + ch] = llcur[c];
-        }
+        for (int c = 0; c < C; ++c)
+            if (on[c]) a.ll[(size_t)g * S + chl[c]] = llcur[c];
     }
 }
 
@@ -681,24 +805,22 @@ __global__ void __launch_bounds__(256) eval_kernel(const SweepArgs a) {
     for (int g = g0; g < g1; ++g) {
         const int R = a.group_nobs[g];
         const T* blk = fits ? tile + (a.group_off[g] - e0) : nullptr;
-        T th[C][P];
+        typename Obj::template Work<C, T> w;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            const int ch = cbase + 32 * c;
-            const bool on = ch < a.n_chains;
+            const int ch = min(cbase + 32 * c, a.n_chains - 1);
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-                double v = 1.0;
-                if (on) v = a.pooled_theta ? a.pooled_theta[(size_t)p * S + ch] : a.theta[((size_t)p * a.G + g) * S + ch];
-                th[c][p] = Obj::template local<T>(p, v, a.obj_const, g);
+                const double v = a.pooled_theta ? a.pooled_theta[(size_t)p * S + ch] : a.theta[((size_t)p * a.G + g) * S + ch];
+                w.set(c, p, Obj::template local<T>(p, v, a.obj_const, g));
             }
         }
         double out[C];
-        group_loglik<Obj, C, T>(a, blk, tile, g, R, mb, parity, th, out);
+        group_loglik<Obj, C, T, true>(a, blk, tile, g, R, mb, parity, w, out);
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const int ch = cbase + 32 * c;
-            if (ch < a.n_chains) a.out_ll[(size_t)g * S + ch] = Obj::finish(out[c], Obj::template aux<T>(R, th[c]));
+            if (ch < a.n_chains) a.out_ll[(size_t)g * S + ch] = Obj::finish(out[c], Obj::template aux<C, T>(R, w, c));
         }
     }
 }
@@ -838,7 +960,7 @@ __global__ void snapshot_kernel(int P, int G, int partial, int n_chains, int S, 
     store_row[(size_t)col * S + ch] = (TS)v;
 }
 
-__global__ void pooled_nll_kernel(int G, int S, const double* ll, double* out) {
+static __global__ void pooled_nll_kernel(int G, int S, const double* ll, double* out) {
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= S) return;
     double s = 0.0;

@@ -8,8 +8,8 @@
 #include <string>
 #include <vector>
 
-#include "mcmcn_device.cuh"
 #include "mcmcn_host.h"
+#include "mcmcn_registry.h"
 
 namespace mcmcn {
 
@@ -27,54 +27,25 @@ void set_error(const char* fmt, ...) {
 static const int kTileCapBytes = 64 * 1024;
 
 // ---------------------------------------------------------------- kernel registry
-typedef void (*sweep_fn)(const SweepArgs);
-typedef void (*pointwise_fn)(const SweepArgs, const long long*, double*);
-
-struct KernelSet {
-    int objective, P, K, precision;
-    int c_wide;                 // chains per lane of the wide variant
-    sweep_fn sweep_wide, sweep_wide_b1, sweep_one;
-    sweep_fn eval_wide, eval_one;
-    pointwise_fn pointwise;
-    int elem_bytes;
-};
-
-#define MCMCN_SET(OBJ_ID, OBJ, KK, PREC, T, CW)                                                        \
-    {OBJ_ID, OBJ::P, KK, PREC, CW, sweep_kernel<OBJ, CW, T, 2>, sweep_kernel<OBJ, CW, T, 1>, sweep_kernel<OBJ, 1, T, 1>,                  \
-     eval_kernel<OBJ, CW, T>, eval_kernel<OBJ, 1, T>, pointwise_kernel<OBJ, T>, (int)sizeof(T)}
-
-static const KernelSet kSets[] = {
-    MCMCN_SET(MCMCN_OBJ_LINEAR_REGRESSION, LinReg<1>, 1, 32, float, 4),
-    MCMCN_SET(MCMCN_OBJ_LINEAR_REGRESSION, LinReg<1>, 1, 64, double, 2),
-    MCMCN_SET(MCMCN_OBJ_LINEAR_REGRESSION, LinReg<2>, 2, 32, float, 4),
-    MCMCN_SET(MCMCN_OBJ_LINEAR_REGRESSION, LinReg<2>, 2, 64, double, 2),
-    MCMCN_SET(MCMCN_OBJ_LINEAR_REGRESSION, LinReg<4>, 4, 32, float, 4),
-    MCMCN_SET(MCMCN_OBJ_LINEAR_REGRESSION, LinReg<4>, 4, 64, double, 2),
-    MCMCN_SET(MCMCN_OBJ_LINEAR_REGRESSION, LinReg<8>, 8, 32, float, 4),
-    MCMCN_SET(MCMCN_OBJ_LINEAR_REGRESSION, LinReg<8>, 8, 64, double, 2),
-    MCMCN_SET(MCMCN_OBJ_BERNOULLI_LOGIT, Logit, 0, 32, float, 4),
-    MCMCN_SET(MCMCN_OBJ_BERNOULLI_LOGIT, Logit, 0, 64, double, 2),
-    MCMCN_SET(MCMCN_OBJ_GAUSSIAN_DISTRIBUTION, GaussDist<1>, 0, 32, float, 4),
-    MCMCN_SET(MCMCN_OBJ_GAUSSIAN_DISTRIBUTION, GaussDist<1>, 0, 64, double, 2),
-    MCMCN_SET(MCMCN_OBJ_GAUSSIAN_DISTRIBUTION, GaussDist<2>, 0, 32, float, 4),
-    MCMCN_SET(MCMCN_OBJ_GAUSSIAN_DISTRIBUTION, GaussDist<2>, 0, 64, double, 2),
-    MCMCN_SET(MCMCN_OBJ_GAUSSIAN_DISTRIBUTION, GaussDist<3>, 0, 32, float, 4),
-    MCMCN_SET(MCMCN_OBJ_GAUSSIAN_DISTRIBUTION, GaussDist<3>, 0, 64, double, 2),
-    MCMCN_SET(MCMCN_OBJ_GAUSSIAN_DISTRIBUTION, GaussDist<4>, 0, 32, float, 4),
-    MCMCN_SET(MCMCN_OBJ_GAUSSIAN_DISTRIBUTION, GaussDist<4>, 0, 64, double, 2),
-};
-
 static const KernelSet* find_set(int objective, int P, int K, int precision) {
-    for (const KernelSet& s : kSets)
-        if (s.objective == objective && s.P == P && s.precision == precision &&
-            (objective != MCMCN_OBJ_LINEAR_REGRESSION || s.K == K))
-            return &s;
+    typedef const KernelSet* (*getter)(int*);
+    static const getter getters[] = {sets_linreg_a, sets_linreg_b, sets_linreg_c, sets_logit, sets_gauss};
+    for (getter get : getters) {
+        int n = 0;
+        const KernelSet* sets = get(&n);
+        for (int i = 0; i < n; ++i) {
+            const KernelSet& s = sets[i];
+            if (s.objective == objective && s.P == P && s.precision == precision &&
+                (objective != MCMCN_OBJ_LINEAR_REGRESSION || s.K == K))
+                return &s;
+        }
+    }
     return nullptr;
 }
 
 // ---------------------------------------------------------------- launch geometry
 struct Geometry {
-    bool wide;
+    bool wide, all_fit;
     int C, nw;
     dim3 grid, block;
     size_t smem;
@@ -100,6 +71,7 @@ static Geometry geometry(const KernelSet* ks, const mcmcn_model* m, int n_chains
     g.grid = dim3((unsigned)m->n_tasks, (unsigned)gy, 1);
     g.block = dim3(32u * g.nw, 1, 1);
     long long bytes = (long long)max_task_elems(m) * ks->elem_bytes;
+    g.all_fit = bytes <= kTileCapBytes;
     if (bytes > kTileCapBytes) bytes = kTileCapBytes;
     if (bytes < 16) bytes = 16;
     g.smem = (size_t)((bytes + 127) & ~127LL);
@@ -179,10 +151,13 @@ int mcmcn_run(const mcmcn_model* m, const mcmcn_state* s, const mcmcn_run_args* 
     SweepArgs a;
     fill_args(a, ks, m, s);
     const Geometry g = geometry(ks, m, s->n_chains);
-    // MCMCN_MINB=1 selects the variant compiled without the 128-register cap (tuning knob)
-    const char* minb = getenv("MCMCN_MINB");
-    const sweep_fn fn = g.wide ? ((minb && minb[0] == '1') ? ks->sweep_wide_b1 : ks->sweep_wide) : ks->sweep_one;
-    rc = set_smem_attr((const void*)fn, g.smem);
+    // production variants (pooling mode and burn-in bookkeeping folded at compile time) when
+    // there is no tape, no trace and every task fits the tile; the general kernel otherwise
+    const bool fast = g.wide && g.all_fit && !r->tape_z && !r->trace_ll && !r->tape_accept &&
+                      !(r->use_lprior_override && partial) && !getenv("MCMCN_GENERAL");
+    const sweep_fn general = g.wide ? ks->sweep_wide : ks->sweep_one;
+    rc = set_smem_attr((const void*)general, g.smem);
+    for (int f = 0; f < 4 && !rc; ++f) rc = set_smem_attr((const void*)ks->sweep_fast[f], g.smem);
     if (rc) return rc;
 
     const size_t S = (size_t)s->stride;
@@ -221,6 +196,7 @@ int mcmcn_run(const mcmcn_model* m, const mcmcn_state* s, const mcmcn_run_args* 
         a.tr_diff = r->trace_diff ? r->trace_diff + it * per_iter : nullptr;
         a.tr_acc = r->trace_accept ? r->trace_accept + it * per_iter : nullptr;
         if (a.tr_ll && !(a.tr_lp && a.tr_diff && a.tr_acc)) { set_error("trace arrays go together"); return MCMCN_ERR_INVALID; }
+        const sweep_fn fn = fast ? ks->sweep_fast[(partial ? MCMCN_F_PARTIAL : 0) | (a.count ? MCMCN_F_COUNT : 0)] : general;
         tic(0);
         fn<<<g.grid, g.block, g.smem, stream>>>(a);
         toc();

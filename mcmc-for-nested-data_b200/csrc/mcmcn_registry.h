@@ -1,0 +1,37 @@
+// mcmcn_registry.h -- table of ahead-of-time compiled kernel sets (one per objective shape and
+// precision).  The instantiations are spread over several translation units so that nvcc
+// compiles them in parallel; mcmcn_kernels.cu looks them up.
+#pragma once
+
+#include "mcmcn_device.cuh"
+
+namespace mcmcn {
+
+typedef void (*sweep_fn)(const SweepArgs);
+typedef void (*pointwise_fn)(const SweepArgs, const long long*, double*);
+
+struct KernelSet {
+    int objective, P, K, precision;
+    int c_wide;                 // chains per lane of the wide variant
+    sweep_fn sweep_fast[4];     // wide, production: index = MCMCN_F_PARTIAL | MCMCN_F_COUNT
+    sweep_fn sweep_wide;        // wide, general (replay tapes, traces, streamed groups)
+    sweep_fn sweep_one;         // one chain per lane, general
+    sweep_fn eval_wide, eval_one;
+    pointwise_fn pointwise;
+    int elem_bytes;
+};
+
+#define MCMCN_SET(OBJ_ID, OBJ, KK, PREC, T, CW)                                                          \
+    {OBJ_ID, OBJ::P, KK, PREC, CW,                                                                       \
+     {sweep_kernel<OBJ, CW, T, 2, 0>, sweep_kernel<OBJ, CW, T, 2, 1>, sweep_kernel<OBJ, CW, T, 2, 2>,    \
+      sweep_kernel<OBJ, CW, T, 2, 3>},                                                                   \
+     sweep_kernel<OBJ, CW, T, 2, -1>, sweep_kernel<OBJ, 1, T, 1, -1>,                                    \
+     eval_kernel<OBJ, CW, T>, eval_kernel<OBJ, 1, T>, pointwise_kernel<OBJ, T>, (int)sizeof(T)}
+
+const KernelSet* sets_linreg_a(int* n);
+const KernelSet* sets_linreg_b(int* n);
+const KernelSet* sets_linreg_c(int* n);
+const KernelSet* sets_logit(int* n);
+const KernelSet* sets_gauss(int* n);
+
+}  // namespace mcmcn
