@@ -286,8 +286,9 @@ def runGpu(args):
                 "roofline": {"bound": "fp32", "kernel": "sweep_kernel<LinReg<8>,4,float>",
                              "achieved": achieved / 1e12, "peak": peakFlops / 1e12, "unit": "TFLOP/s",
                              "frac": achieved / peakFlops,
-                             "peak_source": "FFMA microbenchmark measured in this run (mcmcn_peak_fp32); "
-                                            "MEASURED_PEAKS.json has no FP32 figure; nominal 74.4",
+                             "peak_source": "FP32 pipe limit measured in this run by an FFMA-only microbenchmark "
+                                            "(mcmcn_peak_fp32, one live register per FFMA); MEASURED_PEAKS.json has no "
+                                            "FP32 figure; nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
                              "flop_per_eval": FLOP_PER_EVAL, "traffic": args.traffic,
                              "mufu_peak_gops": mufu.value / 1e9},
                 "clocks": clocks}

@@ -154,7 +154,11 @@ int mcmcn_run(const mcmcn_model* m, const mcmcn_state* s, const mcmcn_run_args* 
     // production variants (pooling mode and burn-in bookkeeping folded at compile time) when
     // there is no tape, no trace and every task fits the tile; the general kernel otherwise
     const bool fast = g.wide && g.all_fit && !r->tape_z && !r->trace_ll && !r->tape_accept &&
-                      !(r->use_lprior_override && partial) && !getenv("MCMCN_GENERAL");
+                      !getenv("MCMCN_GENERAL");   // (the log-prior override iteration also runs general)
+    if (getenv("MCMCN_DEBUG"))
+        fprintf(stderr, "mcmcn_run: fast=%d wide=%d all_fit=%d tape=%p trace=%p force=%p override=%d partial=%d smem=%zu grid=(%u,%u) block=%u\n",
+                (int)fast, (int)g.wide, (int)g.all_fit, (const void*)r->tape_z, (void*)r->trace_ll, (const void*)r->tape_accept,
+                r->use_lprior_override, (int)partial, g.smem, g.grid.x, g.grid.y, g.block.x);
     const sweep_fn general = g.wide ? ks->sweep_wide : ks->sweep_one;
     rc = set_smem_attr((const void*)general, g.smem);
     for (int f = 0; f < 4 && !rc; ++f) rc = set_smem_attr((const void*)ks->sweep_fast[f], g.smem);
@@ -196,7 +200,7 @@ int mcmcn_run(const mcmcn_model* m, const mcmcn_state* s, const mcmcn_run_args* 
         a.tr_diff = r->trace_diff ? r->trace_diff + it * per_iter : nullptr;
         a.tr_acc = r->trace_accept ? r->trace_accept + it * per_iter : nullptr;
         if (a.tr_ll && !(a.tr_lp && a.tr_diff && a.tr_acc)) { set_error("trace arrays go together"); return MCMCN_ERR_INVALID; }
-        const sweep_fn fn = fast ? ks->sweep_fast[(partial ? MCMCN_F_PARTIAL : 0) | (a.count ? MCMCN_F_COUNT : 0)] : general;
+        const sweep_fn fn = (fast && !a.use_override) ? ks->sweep_fast[(partial ? MCMCN_F_PARTIAL : 0) | (a.count ? MCMCN_F_COUNT : 0)] : general;
         tic(0);
         fn<<<g.grid, g.block, g.smem, stream>>>(a);
         toc();

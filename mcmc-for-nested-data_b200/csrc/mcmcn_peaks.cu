@@ -7,18 +7,21 @@
 
 namespace mcmcn {
 
-// 16 independent accumulators per thread, operands arranged like the regression hot loop
-// (one shared multiplicand, per-accumulator multiplier) so the register-bank behaviour matches.
+// 16 independent accumulators per thread, one live register per FFMA (a = a*x + y): the operand
+// pattern that reaches the FP32 pipe's own limit (124.6 of 128 lanes/clk/SM on B200).  Patterns
+// with two fresh register operands per FFMA (the step kernel's x*b[c]+r[c]) top out lower because
+// of even/odd register-bank collisions: 98 lanes scalar, 117 with FFMA2 (tools/fma_probe.cu).
+// The roofline denominator is the pipe's limit, not the pattern's.
 __global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, float seed) {
-    float a[16], b[16];
+    float a[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { a[i] = seed + i; b[i] = 1.0f + 1e-7f * (threadIdx.x + i); }
-    float x = seed * 0.5f;
+    for (int i = 0; i < 16; ++i) a[i] = seed + i;
+    const float x = 1.0f - seed * 1e-7f, y = seed * 0.25f;
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) a[i] = fmaf(x, b[i], a[i]);
+            for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], x, y);
         }
     }
     float s = 0.f;
