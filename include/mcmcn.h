@@ -193,6 +193,16 @@ int mcmcn_diag_moments(const double* x, int64_t n_keys, int32_t m, int32_t n,
  * out[k][t] = sum_j sum_{i>=t} (x[k][j][i]-x[k][j][i-t])^2  (numerator of :189-194) */
 int mcmcn_diag_variogram(const double* x, int64_t n_keys, int32_t m, int32_t n,
                          double* out, void* stream);
+/* B, W, vhat, rhat per key from the half-chain moments (:158-187, :216-224): out device [n_keys][4] */
+int mcmcn_diag_rhat(const double* mean, const double* var, int64_t n_keys, int32_t m, int32_t n,
+                    double* out, void* stream);
+/* autocorrelation, truncation and effective sample size per key (:196-208, :232-255) from the
+ * variogram numerators and the [n_keys][4] output of mcmcn_diag_rhat; rho_out (device
+ * [n_keys][n]) may be NULL; ess_out is device [n_keys]. m is the TOTAL number of half-chains. */
+int mcmcn_diag_ess(const double* vario, const double* rhat4, int64_t n_keys, int32_t m, int32_t n,
+                   double* rho_out, double* ess_out, void* stream);
+/* mean of each contiguous row of `len` doubles (Summary's mean over groups, :466-470) */
+int mcmcn_diag_row_mean(const double* x, int64_t rows, int64_t len, double* out, void* stream);
 /* in-place ascending sort of each key's m*n pooled draws (for median / HDI, :419-427) */
 int mcmcn_diag_sort_keys(double* x, int64_t n_keys, int64_t len, void* stream);
 /* numpy.median and computeHpdInterval (:766-776) on sorted keys: out device [n_keys][3] =

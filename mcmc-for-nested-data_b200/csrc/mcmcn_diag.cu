@@ -103,6 +103,66 @@ __global__ void median_hdi_kernel(const double* __restrict__ s, long long len, l
     }
 }
 
+// B, W, vhat, rhat of one key from its half-chain means and variances (:158-187, :216-224).
+// One warp per key; sums over the m half-chains are taken lane-strided then shuffled.
+__global__ void rhat_kernel(const double* __restrict__ mean, const double* __restrict__ var, long long n_keys, int m,
+                            int n, double* __restrict__ out) {
+    const long long key = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (key >= n_keys) return;
+    const int lane = threadIdx.x & 31;
+    const double* mu = mean + key * m;
+    const double* vr = var + key * m;
+    double s = 0.0, w = 0.0;
+    for (int j = lane; j < m; j += 32) { s += mu[j]; w += vr[j]; }
+    const double grand = warp_sum(s) / (double)m;
+    const double W = warp_sum(w) / (double)m;                        // numpy.mean(numpy.var(rows, ddof=1))
+    double q = 0.0;
+    for (int j = lane; j < m; j += 32) { const double d = mu[j] - grand; q = fma(d, d, q); }
+    const double B = (double)n * (warp_sum(q) / (double)(m - 1));    // n * numpy.var(row means, ddof=1)
+    if (lane == 0) {
+        const double vhat = W * (double)(n - 1) / (double)n + B / (double)n;
+        double* o = out + key * 4;
+        o[0] = B; o[1] = W; o[2] = vhat; o[3] = sqrt(vhat / W);
+    }
+}
+
+// rho_t = 1 - V_t / (2 vhat) for every lag (:196-208), truncation at the first even t with
+// rho_{t+1} + rho_{t+2} < 0 (:241-251) and ESS = m n / (1 + 2 sum_{t<=T} rho_t) with the sum
+// starting at lag 0 (:253-255).  One block per key; rho is staged in shared memory.
+__global__ void ess_kernel(const double* __restrict__ vnum, const double* __restrict__ rh, int m, int n,
+                           double* __restrict__ rho_out, double* __restrict__ ess) {
+    extern __shared__ double rho[];
+    const long long key = blockIdx.x;
+    const double vhat = rh[key * 4 + 2];
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const double V = vnum[key * n + t] / ((double)m * (double)(n - t));
+        const double r = 1.0 - V / (2.0 * vhat);
+        rho[t] = r;
+        if (rho_out) rho_out[key * n + t] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int T = n - 1;
+        for (int t = 0; t < n - 2; t += 2)
+            if (rho[t + 1] + rho[t + 2] < 0.0) { T = t; break; }
+        double s = 0.0;
+        for (int t = 0; t <= T; ++t) s += rho[t];
+        ess[key] = ((double)m * (double)n) / (1.0 + 2.0 * s);
+    }
+}
+
+// mean of each contiguous row of `len` doubles (Summary, :466-470); one warp per row
+__global__ void row_mean_kernel(const double* __restrict__ x, long long rows, long long len, double* __restrict__ out) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const double* p = x + row * len;
+    double s = 0.0;
+    for (long long i = lane; i < len; i += 32) s += p[i];
+    s = warp_sum(s);
+    if (lane == 0) out[row] = s / (double)len;
+}
+
 }  // namespace mcmcn
 
 using namespace mcmcn;
@@ -128,6 +188,33 @@ int mcmcn_diag_variogram(const double* x, int64_t n_keys, int32_t m, int32_t n, 
     const int threads = half < 128 ? ((half + 31) & ~31) : 128;
     const dim3 grid((unsigned)n_keys, (unsigned)((half + threads - 1) / threads), 1);
     variogram_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(x, m, n, out);
+    CK(cudaGetLastError());
+    return MCMCN_OK;
+}
+
+int mcmcn_diag_rhat(const double* mean, const double* var, int64_t n_keys, int32_t m, int32_t n, double* out, void* stream) {
+    if (!mean || !var || !out || n_keys < 1 || m < 2 || n < 2) { set_error("bad diag_rhat args"); return MCMCN_ERR_INVALID; }
+    const int wpb = 8;
+    rhat_kernel<<<(unsigned)((n_keys + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(mean, var, n_keys, m, n, out);
+    CK(cudaGetLastError());
+    return MCMCN_OK;
+}
+
+int mcmcn_diag_ess(const double* vario, const double* rhat4, int64_t n_keys, int32_t m, int32_t n, double* rho_out,
+                   double* ess_out, void* stream) {
+    if (!vario || !rhat4 || !ess_out || n_keys < 1 || m < 1 || n < 3) { set_error("bad diag_ess args"); return MCMCN_ERR_INVALID; }
+    const size_t smem = sizeof(double) * (size_t)n;
+    if (smem > 200 * 1024) { set_error("n=%d draws per half-chain exceed the shared-memory buffer", n); return MCMCN_ERR_UNSUPPORTED; }
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(ess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ess_kernel<<<(unsigned)n_keys, 128, smem, (cudaStream_t)stream>>>(vario, rhat4, m, n, rho_out, ess_out);
+    CK(cudaGetLastError());
+    return MCMCN_OK;
+}
+
+int mcmcn_diag_row_mean(const double* x, int64_t rows, int64_t len, double* out, void* stream) {
+    if (!x || !out || rows < 1 || len < 1) { set_error("bad diag_row_mean args"); return MCMCN_ERR_INVALID; }
+    const int wpb = 8;
+    row_mean_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(x, rows, len, out);
     CK(cudaGetLastError());
     return MCMCN_OK;
 }

@@ -92,6 +92,11 @@ PROTOTYPES = {
                                           c_void_p, c_void_p, c_void_p]),
     "mcmcn_diag_variogram": (ctypes.c_int, [c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                             c_void_p, c_void_p]),
+    "mcmcn_diag_rhat": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                       c_void_p, c_void_p]),
+    "mcmcn_diag_ess": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                      c_void_p, c_void_p, c_void_p]),
+    "mcmcn_diag_row_mean": (ctypes.c_int, [c_void_p, ctypes.c_int64, ctypes.c_int64, c_void_p, c_void_p]),
     "mcmcn_diag_sort_keys": (ctypes.c_int, [c_void_p, ctypes.c_int64, ctypes.c_int64, c_void_p]),
     "mcmcn_diag_median_hdi": (ctypes.c_int, [c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                              c_void_p, c_void_p]),

@@ -1,0 +1,200 @@
+"""GPU tests of the drop-in modules (posteriorSampling.samplePosterior,
+sampleDiagnosis.diagnoseSamples / Diagnostic / Summary / computeHpdInterval) through the
+product package, checked against the reference's golden outputs and the CPU oracle."""
+
+import json
+import os
+import shutil
+
+import numpy
+import pytest
+import scipy.stats
+
+from conftest import GOLDEN, goldenPath, loadGolden, oracleObjectiveFromMeta
+import parity
+from oracle import diagnosis_oracle as do
+from oracle import posterior_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+DIAG_CASES = ["reg_partial", "reg_none", "reg_complete", "dist_none", "dist_complete",
+              "c1_distribution_partial", "reg_ragged_partial"]
+
+
+def _stage(case, tmp_path):
+    """Copy a golden case's reference-written sample files into an output directory."""
+    out = tmp_path / "out"
+    (out / "sample").mkdir(parents=True)
+    for f in os.listdir(os.path.join(GOLDEN, case)):
+        if f.startswith("sample.") and f.endswith(".csv"):
+            shutil.copy(os.path.join(GOLDEN, case, f), out / "sample" / f)
+    return str(out)
+
+
+@pytest.mark.parametrize("case", DIAG_CASES)
+def test_diagnostic_matches_reference_within_1e10(case, tmp_path):
+    """north star: diagnoseSamples within 1e-10 on an identical sample array."""
+    import sampleDiagnosis as sd
+    out = _stage(case, tmp_path)
+    with open(goldenPath(case, "diag.json")) as h:
+        ref = json.load(h)
+    d = sd.Diagnostic(out + "/sample/")
+    assert d._m == ref["m"] and d._n == ref["n"]
+    assert d.partiallyPooled == ref["partiallyPooled"] and d.completelyPooled == ref["completelyPooled"]
+    for k in ref["rhat"]:
+        numpy.testing.assert_allclose(d.rhat[k], float(ref["rhat"][k]), rtol=1e-10)
+        numpy.testing.assert_allclose(d.effectiveN[k], float(ref["effectiveN"][k]), rtol=1e-10)
+        numpy.testing.assert_allclose(d.median[k], float(ref["median"][k]), rtol=1e-10, atol=1e-300)
+        numpy.testing.assert_allclose(d.hdi[k][0], float(ref["hdi"][k][0]), rtol=1e-10, atol=1e-300)
+        numpy.testing.assert_allclose(d.hdi[k][1], float(ref["hdi"][k][1]), rtol=1e-10, atol=1e-300)
+
+
+@pytest.mark.parametrize("case", DIAG_CASES)
+def test_diagnoseSamples_writes_the_reference_files(case, tmp_path, capsys):
+    import sampleDiagnosis as sd
+    out = _stage(case, tmp_path)
+    sd.diagnoseSamples(out, nFigures=0)
+    printed = capsys.readouterr().out
+    for name in ("diagnosticAssessment.csv", "diagnosticAssessmentHyperOnly.csv",
+                 "diagnosticAssessmentIndividual.csv"):
+        ref = goldenPath(case, name)
+        got = os.path.join(out, "diagnostic", name)
+        assert os.path.exists(ref) == os.path.exists(got), name
+        if os.path.exists(ref):
+            assert open(ref).read() == open(got).read(), name
+    assert open(goldenPath(case, "summary.csv")).read() == open(os.path.join(out, "sample", "summary.csv")).read()
+    assert printed == open(goldenPath(case, "diagnose.stdout.txt")).read()
+
+
+def test_computeHpdInterval_matches_reference_formula():
+    import sampleDiagnosis as sd
+    rs = numpy.random.RandomState(3)
+    for n in (2, 3, 10, 101, 4000):
+        x = rs.normal(size=n)
+        x[: n // 3] = numpy.round(x[: n // 3], 1)          # ties
+        got = sd.computeHpdInterval(x, 95)
+        ref = do.computeHpdInterval(x, 95)
+        assert got[0] == ref[0] and got[1] == ref[1]
+
+
+def _regCase():
+    meta = loadGolden("reg_partial")
+    obj, prior = oracleObjectiveFromMeta(meta)
+    return meta, obj, prior
+
+
+@pytest.mark.parametrize("pooling", ["partial", "none", "complete"])
+def test_start_state_equals_reference_chain(pooling):
+    """Engine.initialise draws from each chain's MT19937 stream in the reference's order."""
+    from engine import Engine
+    meta, obj, prior = _regCase()
+    names = tuple(meta["parameterName"])
+    nC = 5
+    eng = Engine(parity.deviceObjective(obj, 10, "fp64"), 10, 10, pooling, nC, priorDistribution=prior, chainId0=2)
+    eng.initialise(names, meta["startingPointValueRange"], False)
+    st = eng.getState()
+    for c in range(nC):
+        oc = po.OracleChain(2 + c, 2 + c, 100, 50, names, 10, 10, pooling, obj, prior, False,
+                            meta["startingPointValueRange"])
+        numpy.testing.assert_array_equal(st["theta"][:, :, c], oc.value)
+        if pooling == "partial":
+            numpy.testing.assert_array_equal(st["mu"][:, c], oc.mu)
+            numpy.testing.assert_array_equal(st["sigma2"][:, c], oc.sigma2)
+            numpy.testing.assert_allclose(st["ll"][:, c], oc.LL, rtol=1e-12)
+        else:
+            assert numpy.isnan(st["ll"][:, c]).all()
+            numpy.testing.assert_allclose(st["lprior"][:, :, c], oc.logPrior, rtol=1e-14)
+
+
+def test_mle_start_close_to_scipy_nelder_mead():
+    from engine import Engine
+    meta, obj, prior = _regCase()
+    names = tuple(meta["parameterName"])
+    eng = Engine(parity.deviceObjective(obj, 10, "fp64"), 10, 10, "partial", 3, chainId0=0)
+    eng.initialise(names, meta["startingPointValueRange"], True)
+    for c in range(3):
+        oc = po.OracleChain(c, c, 100, 50, names, 10, 10, "partial", obj, prior, True,
+                            meta["startingPointValueRange"])
+        numpy.testing.assert_allclose(eng.startingPoint[:, c], oc.startingPoint, rtol=1e-6, atol=1e-6)
+
+
+def test_samplePosterior_free_running_matches_oracle_within_mc_error(tmp_path):
+    """Free-running (Philox) posterior means and SDs agree with the oracle within MC error."""
+    import posteriorSampling as ps
+    import sampleDiagnosis as sd
+    from objectives import Objective
+    meta, obj, prior = _regCase()
+    names = tuple(meta["parameterName"])
+    nIter, nSamples, nChains = 4000, 1000, 16
+    out = str(tmp_path / "gpu")
+    ps.samplePosterior(nChains, nIter, nSamples, names, 10, 10, "partial",
+                       Objective.linear_regression(obj.X, obj.y), out, saveLogLikelihood=False,
+                       priorDistribution=prior, startingPointValueRange=meta["startingPointValueRange"],
+                       displayProgress=False)
+    keys, gpu, chains = sd.loadSamples(out + "/sample/")
+    assert gpu.shape == (nChains, 1000, 36) and chains == list(range(nChains))
+    text = open(out + "/sample/sample.3.csv").read().splitlines()
+    assert text[0].startswith("index,chain,b0_mu,b0_sigma2,b0[000],") and text[1].startswith("2000,3,")
+    assert len(text) == 1001 and os.path.exists(out + "/log/samplePosterior.log")
+    # oracle: same model, its own RNG
+    rows = []
+    for c in range(6):
+        oc = po.OracleChain(100 + c, 100 + c, nIter, nSamples, names, 10, 10, "partial", obj, prior, False,
+                            meta["startingPointValueRange"])
+        rows.append(numpy.stack([r[1] for r in oc.run()]))
+    ora = numpy.stack(rows)                                    # [chains][rows][keys]
+    gm, om = gpu.mean(axis=(0, 1)), ora.mean(axis=(0, 1))
+    gs, os_ = gpu.std(axis=(0, 1)), ora.std(axis=(0, 1))
+    # Monte-Carlo standard error from between-chain spread of the chain means (both arms)
+    se = numpy.sqrt(gpu.mean(axis=1).var(axis=0, ddof=1) / nChains + ora.mean(axis=1).var(axis=0, ddof=1) / 6)
+    z = numpy.abs(gm - om) / numpy.maximum(se, 1e-12)
+    assert numpy.median(z) < 1.5 and z.max() < 6.0, (z.max(), keys[int(z.argmax())])
+    numpy.testing.assert_allclose(gs, os_, rtol=0.35)
+
+
+def test_samplePosterior_loglikelihood_file_and_binary_store(tmp_path, monkeypatch):
+    import posteriorSampling as ps
+    import sampleDiagnosis as sd
+    from objectives import Objective
+    meta, obj, prior = _regCase()
+    names = tuple(meta["parameterName"])
+    out = str(tmp_path / "csv")
+    ps.samplePosterior(3, 200, 50, names, 10, 10, "none", Objective.linear_regression(obj.X, obj.y, "fp64"),
+                       out, saveLogLikelihood=True, priorDistribution=prior,
+                       startingPointValueRange=meta["startingPointValueRange"], displayProgress=False)
+    keys, smp, _ = sd.loadSamples(out + "/sample/")
+    ll = numpy.loadtxt(out + "/sample/logLikelihood.1.csv", delimiter=",")
+    assert ll.shape == (50, 100)
+    # pointwise log-likelihood of the retained state, recomputed by the oracle objective
+    theta = smp[1, -1].reshape(3, 10)
+    ref = obj([numpy.repeat(theta[p], 10) for p in range(3)])
+    numpy.testing.assert_allclose(ll[-1], ref, atol=2e-6)
+    # the same run forced into the binary store
+    monkeypatch.setattr(ps, "CSV_VALUE_LIMIT", 0)
+    out2 = str(tmp_path / "bin")
+    ps.samplePosterior(3, 200, 50, names, 10, 10, "none", Objective.linear_regression(obj.X, obj.y, "fp64"),
+                       out2, saveLogLikelihood=False, priorDistribution=prior,
+                       startingPointValueRange=meta["startingPointValueRange"], displayProgress=False)
+    assert os.path.exists(out2 + "/sample/manifest.json")
+    keys2, smp2, _ = sd.loadSamples(out2 + "/sample/")
+    assert keys2 == keys
+    numpy.testing.assert_allclose(smp2, smp, rtol=1e-6, atol=1e-6)     # float32 store, same Philox streams
+    d = sd.Diagnostic(out2 + "/sample/")
+    assert set(d.rhat) == set(keys)
+
+
+def test_samplePosterior_argument_errors(tmp_path):
+    import posteriorSampling as ps
+    from objectives import Objective
+    meta, obj, prior = _regCase()
+    names = tuple(meta["parameterName"])
+    handle = Objective.linear_regression(obj.X, obj.y)
+    with pytest.raises(TypeError):
+        ps.samplePosterior(1, 10, 5, names, 10, 10, "partial", lambda p: p, str(tmp_path / "a"), displayProgress=False)
+    with pytest.raises(Exception):
+        ps.samplePosterior(1, 10, 5, names, 10, 10, "hierarchical", handle, str(tmp_path / "b"), displayProgress=False)
+    with pytest.raises(Exception):
+        ps.samplePosterior(1, 5, 10, names, 10, 10, "partial", handle, str(tmp_path / "c"), displayProgress=False)
+    with pytest.raises(ValueError, match="Invalid prior"):
+        ps.samplePosterior(1, 10, 5, names, 10, 10, "none", handle, str(tmp_path / "d"),
+                           startingPointValueRange=meta["startingPointValueRange"], displayProgress=False)

@@ -1,0 +1,224 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol include/mcmcn.h declares,
+the ctypes structs mirror the C structs, and the host-side logic (schedule, output format,
+data packing, prior mapping, batched Nelder-Mead, start-state search, shard merging over
+gloo with world_size 2) behaves like the reference / oracle.  No kernel is launched here."""
+
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy
+import pytest
+import scipy.optimize
+import scipy.stats
+
+from conftest import GOLDEN, ROOT, PKG, goldenPath, loadGolden, oracleObjectiveFromMeta
+from oracle import posterior_oracle as po
+
+import mcmcn_native as nat
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "mcmcn.h")).read()
+    return sorted(set(re.findall(r"^\s*(?:int|const char\*)\s+(mcmcn_[a-z0-9_]+)\s*\(", text, re.M)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = nat.load()
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), n
+        assert n in nat.PROTOTYPES, "no ctypes prototype for %s" % n
+    assert lib.mcmcn_version() == 100
+    assert lib.mcmcn_tile_capacity_bytes() == 65536
+    assert lib.mcmcn_supported(nat.OBJ_LINEAR_REGRESSION, 9, 8, 32) == 1
+    assert lib.mcmcn_supported(nat.OBJ_LINEAR_REGRESSION, 7, 6, 32) == 0
+
+
+def test_ctypes_structs_mirror_the_header(tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "mcmcn.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(mcmcn_prior), sizeof(mcmcn_model), sizeof(mcmcn_state), sizeof(mcmcn_run_args),'
+                   'offsetof(mcmcn_model, prior), offsetof(mcmcn_run_args, timing));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = list(map(int, subprocess.check_output([str(exe)]).split()))
+    assert got == [ctypes.sizeof(nat.Prior), ctypes.sizeof(nat.Model), ctypes.sizeof(nat.State),
+                   ctypes.sizeof(nat.RunArgs), nat.Model.prior.offset, nat.RunArgs.timing.offset]
+
+
+def test_no_cpu_fallback_and_callable_rejected():
+    import torch
+    from engine import Engine
+    from objectives import Objective
+    with pytest.raises(TypeError):
+        Engine(lambda p: p, 2, 2, "partial", 1)
+    if not torch.cuda.is_available():
+        obj = Objective.bernoulli_logit(numpy.zeros(4), numpy.zeros(4))
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            Engine(obj, 2, 2, "partial", 1)
+    with pytest.raises(TypeError):
+        Objective.bernoulli_logit(numpy.zeros(4), numpy.zeros(4))([[0.0] * 4, [0.0] * 4])
+
+
+def test_burn_thin_and_retained_iterations_follow_the_reference():
+    from engine import burnThin, retainedIterations
+    for nIter, nSamples in [(1000, 100), (2000, 1000), (600, 100), (240, 120), (400, 100), (7, 7), (20000, 1000)]:
+        assert burnThin(nIter, nSamples) == po.burn_thin(nIter, nSamples)
+    assert burnThin(1000, 100) == (500, 5) and burnThin(2000, 1000) == (1000, 1)
+    assert retainedIterations(1000, 500, 5) == list(range(500, 1000, 5))
+    with pytest.raises(Exception):
+        burnThin(5, 10)
+
+
+@pytest.mark.parametrize("case", ["reg_partial", "dist_none", "reg_complete"])
+def test_csv_writer_reproduces_reference_files(case, tmp_path):
+    import pandas
+    import posteriorSampling as ps
+    meta = loadGolden(case)
+    ref = goldenPath(case, "sample.1.csv")
+    d = pandas.read_csv(ref, float_precision="round_trip")
+    G = 1 if meta["pooling"] == "complete" else meta["nGroups"]
+    header = ps.sampleHeader(meta["parameterName"], G, meta["pooling"])
+    assert header == list(d.columns[2:])
+    out = tmp_path / "sample.1.csv"
+    ps.writeSampleCsv(str(out), 1, header, list(d["index"]), d[header].to_numpy())
+    assert open(ref).read() == out.read_text()
+
+
+def test_regression_packing_is_the_same_residual():
+    from objectives import Objective
+    rs = numpy.random.RandomState(0)
+    nResp = [5, 1, 8, 4, 3]
+    N, K = sum(nResp), 3
+    X, y = rs.normal(size=(N, K)), 100 + rs.normal(size=N)
+    for prec in ("fp32", "fp64"):
+        data, off, nobs, bbar = Objective.linear_regression(X, y, prec).pack(nResp)
+        KP, unit = 4, 4 * 4 + 4
+        bbar = bbar.reshape(len(nResp), K)
+        start = 0
+        for g, r in enumerate(nResp):
+            b = rs.normal(size=K)
+            blk = data[off[g]:off[g + 1]].astype(float).reshape(-1, unit)
+            x = blk[:, :4 * KP].reshape(-1, KP, 4)                      # [quad][k][obs]
+            ne = blk[:, 4 * KP:]                                         # [quad][obs]
+            res = numpy.einsum("qkj,k->qj", x[:, :K, :], b - bbar[g]) + ne
+            want = X[start:start + r] @ b - y[start:start + r]
+            numpy.testing.assert_allclose(res.reshape(-1)[:r], want, rtol=0, atol=2e-5 if prec == "fp32" else 1e-12)
+            assert numpy.all(res.reshape(-1)[r:] == 0)                   # padding contributes nothing
+            start += r
+        assert list(nobs) == nResp and off[-1] == data.size
+
+
+def test_prior_mapping():
+    from engine import priorFromScipy
+    pr = priorFromScipy(scipy.stats.gamma(10))
+    assert pr.family == nat.PRIOR_GAMMA and pr.a == 10 and pr.scale == 1 and pr.loc == 0
+    assert abs(pr.c0 - float(scipy.special.gammaln(10.0))) == 0
+    pr = priorFromScipy(scipy.stats.norm(loc=100, scale=10))
+    assert (pr.family, pr.loc, pr.scale, pr.log_scale) == (nat.PRIOR_NORM, 100.0, 10.0, float(numpy.log(10.0)))
+    assert priorFromScipy(scipy.stats.uniform(-2, 4)).family == nat.PRIOR_UNIFORM
+    with pytest.raises(ValueError):
+        priorFromScipy(scipy.stats.cauchy())
+
+
+class _FakeEngine(object):
+    """Host stand-in for Engine.pooledNll so that the start-up logic runs without a GPU."""
+
+    def __init__(self, f, P, nChains, prior=None):
+        self.f, self.P, self.nChains, self.priorScipy = f, P, nChains, prior
+
+    def pooledNll(self, x):
+        return numpy.array([self.f(x[:, c]) for c in range(x.shape[1])])
+
+
+def test_batched_nelder_mead_equals_scipy():
+    from startpoint import nelderMead
+    A = numpy.array([[3.0, 0.5, 0.1], [0.5, 2.0, 0.3], [0.1, 0.3, 1.0]])
+
+    def f(v):
+        return float((v - 1.5) @ A @ (v - 1.5) + 0.1 * numpy.sum(numpy.cos(3 * v)))
+
+    rs = numpy.random.RandomState(4)
+    x0 = rs.uniform(-3, 3, size=(3, 7))
+    x0[1, 2] = 0.0                                   # exercises the zero-coordinate simplex rule
+    eng = _FakeEngine(f, 3, 7)
+    x, fx, ok = nelderMead(eng, x0, numpy.ones(7, dtype=bool))
+    for c in range(7):
+        res = scipy.optimize.minimize(f, x0[:, c], method="Nelder-Mead")
+        numpy.testing.assert_allclose(x[:, c], res.x, rtol=1e-12, atol=1e-12)
+        assert ok[c] == res.success
+
+
+def test_start_point_search_consumes_the_reference_stream():
+    from startpoint import findStartingPoints
+    meta = loadGolden("reg_none")
+    obj, prior = oracleObjectiveFromMeta(meta)
+    names = tuple(meta["parameterName"])
+
+    def nll(v):
+        with numpy.errstate(all="ignore"):
+            return -numpy.sum(obj([numpy.full(100, t) for t in v]))
+
+    for ranges in (meta["startingPointValueRange"], {"b0": [-1, 1]}):       # second: priors for b1, sigma
+        eng = _FakeEngine(nll, 3, 4, prior)
+        rss = [numpy.random.RandomState(c) for c in range(4)]
+        x = findStartingPoints(eng, rss, names, ranges, False)
+        for c in range(4):
+            oc = po.OracleChain(c, c, 20, 10, names, 10, 10, "none", obj, prior, False, ranges)
+            numpy.testing.assert_array_equal(x[:, c], oc.startingPoint)
+    with pytest.raises(ValueError):
+        findStartingPoints(_FakeEngine(nll, 3, 1, None), [numpy.random.RandomState(0)], names, {"b0": [0, 1]}, False)
+
+
+def _gloo_worker(rank, world, port, tmp):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, PKG)
+    import sampleDiagnosis as sd
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rs = numpy.random.RandomState(11)
+    x = rs.normal(size=(5, 12, 40))                       # [keys][m][n], all chains
+    lo, hi = sd.chainRange(6, rank, world)                # 6 chains = 12 half-chains
+    mine = x[:, 2 * lo:2 * hi, :]
+    mean = torch.from_numpy(mine.mean(axis=2))
+    var = torch.from_numpy(mine.var(axis=2, ddof=1))
+    vario = torch.from_numpy(numpy.stack(
+        [[((mine[k, :, t:] - mine[k, :, :40 - t]) ** 2).sum() for t in range(40)] for k in range(5)]))
+    gm, gv, gvario = sd.mergeShards(mean, var, vario, dist.group.WORLD)
+    numpy.save(os.path.join(tmp, "merged.%d.npy" % rank),
+               numpy.concatenate([gm.numpy().ravel(), gv.numpy().ravel(), gvario.numpy().ravel()]))
+    dist.destroy_process_group()
+
+
+def test_shard_merge_over_gloo_world_size_2(tmp_path):
+    """N > 1 path on CPU: two ranks each hold half of the chains; after the exchange both hold
+    the moments of all half-chains in chain order and identical per-lag sums."""
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a = numpy.load(tmp_path / "merged.0.npy")
+    b = numpy.load(tmp_path / "merged.1.npy")
+    assert numpy.array_equal(a, b)                        # bit-identical on every rank
+    rs = numpy.random.RandomState(11)
+    x = rs.normal(size=(5, 12, 40))
+    mean, var = x.mean(axis=2), x.var(axis=2, ddof=1)
+    vario = numpy.stack([[((x[k, :, t:] - x[k, :, :40 - t]) ** 2).sum() for t in range(40)] for k in range(5)])
+    numpy.testing.assert_array_equal(a[:60], mean.ravel())
+    numpy.testing.assert_array_equal(a[60:120], var.ravel())
+    numpy.testing.assert_allclose(a[120:], vario.ravel(), rtol=1e-13)
+
+
+def test_chain_ranges_partition_the_chains():
+    import sampleDiagnosis as sd
+    for n, w in [(16384, 8), (1024, 3), (7, 2), (8, 8)]:
+        cover = []
+        for r in range(w):
+            lo, hi = sd.chainRange(n, r, w)
+            cover += list(range(lo, hi))
+        assert cover == list(range(n))
