@@ -345,6 +345,9 @@ struct LinReg {
     }
     // Per-chain terms that only change when sigma does: -1/(2 sigma^2) and R*(log sigma + log sqrt(2 pi)).
     struct Aux { double mhalf_inv2, rlog; };
+    static constexpr int AUX_DOUBLES = 2;
+    __device__ static __forceinline__ void aux_put(const Aux& a, double* p, int stride) { p[0] = a.mhalf_inv2; p[stride] = a.rlog; }
+    __device__ static __forceinline__ Aux aux_get(const double* p, int stride) { Aux a; a.mhalf_inv2 = p[0]; a.rlog = p[stride]; return a; }
     template <int C, typename T>
     __device__ static __forceinline__ Aux aux(int R, const Work<C, T>& w, int c) {
         const double sg = w.sigma(c);
@@ -428,6 +431,9 @@ struct Logit {
         }
     }
     struct Aux {};
+    static constexpr int AUX_DOUBLES = 0;
+    __device__ static __forceinline__ void aux_put(const Aux&, double*, int) {}
+    __device__ static __forceinline__ Aux aux_get(const double*, int) { return Aux(); }
     template <int C, typename T>
     __device__ static __forceinline__ Aux aux(int, const Work<C, T>&, int) { return Aux(); }
     __device__ static __forceinline__ bool aux_depends_on(int) { return false; }
@@ -479,6 +485,9 @@ struct GaussDist {
         }
     }
     struct Aux {};
+    static constexpr int AUX_DOUBLES = 0;
+    __device__ static __forceinline__ void aux_put(const Aux&, double*, int) {}
+    __device__ static __forceinline__ Aux aux_get(const double*, int) { return Aux(); }
     template <int C, typename T>
     __device__ static __forceinline__ Aux aux(int, const Work<C, T>&, int) { return Aux(); }
     __device__ static __forceinline__ bool aux_depends_on(int) { return false; }
@@ -500,6 +509,7 @@ struct SweepArgs {
     int P, G;
     int partial;
     int tile_cap_elems;
+    int tile_bytes;               // dynamic shared memory reserved for the tile; parking slots follow
     mcmcn_prior prior[MCMCN_MAX_PARAMS];
     // state
     int n_chains, S;
@@ -575,8 +585,8 @@ __device__ __forceinline__ void group_loglik(const SweepArgs& a, const T* blk, T
 // ---------------------------------------------------------------- the step kernel
 // grid = (tasks, chain blocks); block = NW warps; one warp = 32*C chains of one group at a time.
 // MINB = minimum resident CTAs per SM the register allocation must allow (2 -> at most 128 registers).
-template <class Obj, int C, typename T, int MINB, int F>
-__global__ void __launch_bounds__(256, MINB) sweep_kernel(const SweepArgs a) {
+template <class Obj, int C, typename T, int MINB, int F, int MAXT = 256>
+__global__ void __launch_bounds__(MAXT, MINB) sweep_kernel(const SweepArgs a) {
     constexpr int P = Obj::P;
     constexpr bool GENERAL = F < 0;
     const bool partial = GENERAL ? (a.partial != 0) : ((F & MCMCN_F_PARTIAL) != 0);
@@ -611,32 +621,34 @@ __global__ void __launch_bounds__(256, MINB) sweep_kernel(const SweepArgs a) {
         on[c] = cbase + 32 * c < a.n_chains;
         chl[c] = min(cbase + 32 * c, a.n_chains - 1);
     }
+    // per-thread parking slots in shared memory behind the tile: [field][c][thread], 8 bytes each
+    double* park = reinterpret_cast<double*>(smem_raw + a.tile_bytes);
+    enum { ST_PROP = 0, ST_U, ST_LPPROP, ST_LPCUR, ST_LLCUR, ST_OLD, ST_AUX };
+#define SLOT(f, c) park[((f) * C + (c)) * blockDim.x + threadIdx.x]
 
     for (int g = g0; g < g1; ++g) {
         const int R = a.group_nobs[g];
         const T* blk = fits ? tile + (a.group_off[g] - e0) : nullptr;
 
         typename Obj::template Work<C, T> w;
-        double llcur[C];
-        typename Obj::Aux aux_cur[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
 #pragma unroll
             for (int p = 0; p < P; ++p)
                 w.set(c, p, Obj::template local<T>(p, a.theta[((size_t)p * a.G + g) * S + chl[c]], a.obj_const, g));
-            llcur[c] = a.ll[(size_t)g * S + chl[c]];
-            aux_cur[c] = Obj::template aux<C, T>(R, w, c);
+            SLOT(ST_LLCUR, c) = a.ll[(size_t)g * S + chl[c]];
+            Obj::aux_put(Obj::template aux<C, T>(R, w, c), &SLOT(ST_AUX, c), C * (int)blockDim.x);
         }
 
 #pragma unroll 1
         for (int p = 0; p < P; ++p) {
-            // Written stage by stage over the C chains with selects instead of branches, so that
-            // the C independent dependency chains interleave in one basic block.
+            // Decision code is written stage by stage over the C chains with selects instead of
+            // branches, so the C independent dependency chains interleave in one basic block.
+            // Everything that must survive the observation loop is parked in shared memory
+            // (SLOT), so the loop runs spill-free and nothing after it waits on L2.
             const size_t row = ((size_t)p * a.G + g) * S;
-            double prop[C], uu[C];
-            T old[C];
             {
-                double cur[C], sc[C], z[C];
+                double cur[C], sc[C], z[C], uu[C], prop[C];
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     cur[c] = a.theta[row + chl[c]];
@@ -647,6 +659,11 @@ __global__ void __launch_bounds__(256, MINB) sweep_kernel(const SweepArgs a) {
                     for (int c = 0; c < C; ++c) {
                         prefetch_l1(a.theta + row + (size_t)a.G * S + chl[c]);
                         prefetch_l1(a.scale + row + (size_t)a.G * S + chl[c]);
+                        if (partial) {
+                            prefetch_l1(a.hyper + ((size_t)0 * P + p + 1) * S + chl[c]);
+                            prefetch_l1(a.hyper + ((size_t)3 * P + p + 1) * S + chl[c]);
+                            prefetch_l1(a.hyper + ((size_t)4 * P + p + 1) * S + chl[c]);
+                        }
                     }
                 }
                 if (replay) {
@@ -668,9 +685,38 @@ __global__ void __launch_bounds__(256, MINB) sweep_kernel(const SweepArgs a) {
                     }
                 }
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
+                for (int c = 0; c < C; ++c)
                     prop[c] = __dadd_rn(cur[c], __dmul_rn(sc[c], z[c]));   // numpy.random.normal(value, sd), :304-306
-                    old[c] = w.get(c, p);
+                // log-priors of the proposal and of the current value (pure functions of state
+                // known now; the reference evaluates them after the likelihood, :335, :331)
+                double lp_prop[C], lp_cur[C];
+                if (partial) {
+                    double mu[C], lsd[C], isd[C];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        mu[c] = a.hyper[((size_t)0 * P + p) * S + chl[c]];
+                        lsd[c] = a.hyper[((size_t)3 * P + p) * S + chl[c]];
+                        isd[c] = a.hyper[((size_t)4 * P + p) * S + chl[c]];
+                    }
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        lp_prop[c] = norm_logpdf_inv(prop[c], mu[c], isd[c], lsd[c]);
+                        lp_cur[c] = override_lp ? a.lprior[row + chl[c]] : norm_logpdf_inv(cur[c], mu[c], isd[c], lsd[c]);
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        lp_prop[c] = prior_logpdf(a.prior[p], prop[c]);
+                        lp_cur[c] = a.lprior[row + chl[c]];
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    SLOT(ST_PROP, c) = prop[c];
+                    SLOT(ST_U, c) = uu[c];
+                    SLOT(ST_LPPROP, c) = lp_prop[c];
+                    SLOT(ST_LPCUR, c) = lp_cur[c];
+                    SLOT(ST_OLD, c) = (double)w.get(c, p);
                     w.set(c, p, Obj::template local<T>(p, prop[c], a.obj_const, g));
                 }
             }
@@ -680,44 +726,27 @@ __global__ void __launch_bounds__(256, MINB) sweep_kernel(const SweepArgs a) {
 
             typename Obj::Aux aux_prop[C];
 #pragma unroll
-            for (int c = 0; c < C; ++c) aux_prop[c] = aux_cur[c];
+            for (int c = 0; c < C; ++c) aux_prop[c] = Obj::aux_get(&SLOT(ST_AUX, c), C * (int)blockDim.x);
             if (Obj::aux_depends_on(p)) {
 #pragma unroll
                 for (int c = 0; c < C; ++c) aux_prop[c] = Obj::template aux<C, T>(R, w, c);
             }
-            double llp[C], lp_prop[C], lp_cur[C];
-            if (partial) {
-                double mu[C], lsd[C], isd[C], cur[C];
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    mu[c] = a.hyper[((size_t)0 * P + p) * S + chl[c]];
-                    lsd[c] = a.hyper[((size_t)3 * P + p) * S + chl[c]];
-                    isd[c] = a.hyper[((size_t)4 * P + p) * S + chl[c]];
-                    cur[c] = override_lp ? a.lprior[row + chl[c]] : a.theta[row + chl[c]];
-                }
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    lp_prop[c] = norm_logpdf_inv(prop[c], mu[c], isd[c], lsd[c]);
-                    lp_cur[c] = override_lp ? cur[c] : norm_logpdf_inv(cur[c], mu[c], isd[c], lsd[c]);
-                }
-            } else {
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    lp_prop[c] = prior_logpdf(a.prior[p], prop[c]);
-                    lp_cur[c] = a.lprior[row + chl[c]];
-                }
-            }
             // Parameter.step decision tree, :334-367
-            double diff[C];
+            double llp[C], diff[C], uu[C], lp_prop[C], post_cur[C];
             bool acc_own[C];
             bool exact_any = false;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
+                uu[c] = SLOT(ST_U, c);
+                lp_prop[c] = SLOT(ST_LPPROP, c);
+                post_cur[c] = SLOT(ST_LPCUR, c) + SLOT(ST_LLCUR, c);
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
                 llp[c] = Obj::finish(acc[c], aux_prop[c]);
                 const double post_prop = lp_prop[c] + llp[c];
-                const double post_cur = lp_cur[c] + llcur[c];
-                diff[c] = post_prop - post_cur;
-                const bool b1 = !finite64(post_cur) && finite64(post_prop);
+                diff[c] = post_prop - post_cur[c];
+                const bool b1 = !finite64(post_cur[c]) && finite64(post_prop);
                 const bool test = finite64(llp[c]) && finite64(diff[c]);       // branches 4/5 draw the uniform
                 const int fast = log_u_vs_diff_fast(uu[c], diff[c]);
                 acc_own[c] = b1 || (test && fast > 0);
@@ -726,8 +755,7 @@ __global__ void __launch_bounds__(256, MINB) sweep_kernel(const SweepArgs a) {
             if (exact_any) {                                           // rare: within 1e-6 of the threshold
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    const double post_cur = lp_cur[c] + llcur[c];
-                    const bool b1 = !finite64(post_cur) && finite64(lp_prop[c] + llp[c]);
+                    const bool b1 = !finite64(post_cur[c]) && finite64(lp_prop[c] + llp[c]);
                     if (!b1 && finite64(llp[c]) && finite64(diff[c]) && log_u_vs_diff_fast(uu[c], diff[c]) == 0)
                         acc_own[c] = log(uu[c]) < diff[c];
                 }
@@ -745,13 +773,16 @@ __global__ void __launch_bounds__(256, MINB) sweep_kernel(const SweepArgs a) {
                     }
                     if (forced) accept = a.tape_acc[at] != 0;
                 }
-                if (accept && on[c]) {                               // :369-378, :608-610
-                    a.theta[at] = prop[c];
-                    if (!partial) a.lprior[at] = lp_prop[c];
+                if (accept) {                                        // :369-378, :608-610
+                    if (on[c]) {
+                        a.theta[at] = SLOT(ST_PROP, c);
+                        if (!partial) a.lprior[at] = lp_prop[c];
+                    }
+                    SLOT(ST_LLCUR, c) = llp[c];
+                    Obj::aux_put(aux_prop[c], &SLOT(ST_AUX, c), C * (int)blockDim.x);
+                } else {
+                    w.set(c, p, (T)SLOT(ST_OLD, c));
                 }
-                llcur[c] = accept ? llp[c] : llcur[c];
-                aux_cur[c] = accept ? aux_prop[c] : aux_cur[c];
-                if (!accept) w.set(c, p, old[c]);
                 if (count && on[c]) {
                     unsigned cnt = a.counts[at];
                     cnt += accept ? 1u : 0x10000u;
@@ -779,8 +810,9 @@ __global__ void __launch_bounds__(256, MINB) sweep_kernel(const SweepArgs a) {
         }
 #pragma unroll
         for (int c = 0; c < C; ++c)
-            if (on[c]) a.ll[(size_t)g * S + chl[c]] = llcur[c];
+            if (on[c]) a.ll[(size_t)g * S + chl[c]] = SLOT(ST_LLCUR, c);
     }
+#undef SLOT
 }
 
 // Group log-likelihood of the current (or pooled) parameter values, no proposal.

@@ -48,7 +48,8 @@ struct Geometry {
     bool wide, all_fit;
     int C, nw;
     dim3 grid, block;
-    size_t smem;
+    size_t tile_bytes;          // dynamic shared memory of the observation tile
+    size_t smem;                // tile + parking slots of the step kernel
 };
 
 static int max_task_elems(const mcmcn_model* m) {
@@ -60,13 +61,13 @@ static int max_task_elems(const mcmcn_model* m) {
     return (int)(mx > (1LL << 30) ? (1LL << 30) : mx);
 }
 
-static Geometry geometry(const KernelSet* ks, const mcmcn_model* m, int n_chains) {
+static Geometry geometry(const KernelSet* ks, const mcmcn_model* m, int n_chains, int max_warps = 8) {
     Geometry g;
     g.wide = n_chains >= 32 * ks->c_wide;
     g.C = g.wide ? ks->c_wide : 1;
     const int per_warp = 32 * g.C;
     int warps = (n_chains + per_warp - 1) / per_warp;
-    g.nw = warps < 8 ? warps : 8;
+    g.nw = warps < max_warps ? warps : max_warps;
     const int gy = (warps + g.nw - 1) / g.nw;
     g.grid = dim3((unsigned)m->n_tasks, (unsigned)gy, 1);
     g.block = dim3(32u * g.nw, 1, 1);
@@ -74,7 +75,8 @@ static Geometry geometry(const KernelSet* ks, const mcmcn_model* m, int n_chains
     g.all_fit = bytes <= kTileCapBytes;
     if (bytes > kTileCapBytes) bytes = kTileCapBytes;
     if (bytes < 16) bytes = 16;
-    g.smem = (size_t)((bytes + 127) & ~127LL);
+    g.tile_bytes = (size_t)((bytes + 127) & ~127LL);
+    g.smem = g.tile_bytes + (size_t)ks->park_doubles * g.C * g.block.x * sizeof(double);
     return g;
 }
 
@@ -150,9 +152,14 @@ int mcmcn_run(const mcmcn_model* m, const mcmcn_state* s, const mcmcn_run_args* 
 
     SweepArgs a;
     fill_args(a, ks, m, s);
-    const Geometry g = geometry(ks, m, s->n_chains);
+    // production geometry: 128-thread CTAs (4 warps = 512 chains), 3 per SM at 168 registers, which
+    // keeps the observation loop spill-free; MCMCN_GEOM=2 selects 256-thread CTAs x 2 (128 registers)
+    const char* geom = getenv("MCMCN_GEOM");
+    const bool geom3 = !(geom && geom[0] == '2');
+    const Geometry g = geometry(ks, m, s->n_chains, geom3 ? 4 : 8);
     // production variants (pooling mode and burn-in bookkeeping folded at compile time) when
     // there is no tape, no trace and every task fits the tile; the general kernel otherwise
+    a.tile_bytes = (int)g.tile_bytes;
     const bool fast = g.wide && g.all_fit && !r->tape_z && !r->trace_ll && !r->tape_accept &&
                       !getenv("MCMCN_GENERAL");   // (the log-prior override iteration also runs general)
     if (getenv("MCMCN_DEBUG"))
@@ -162,6 +169,7 @@ int mcmcn_run(const mcmcn_model* m, const mcmcn_state* s, const mcmcn_run_args* 
     const sweep_fn general = g.wide ? ks->sweep_wide : ks->sweep_one;
     rc = set_smem_attr((const void*)general, g.smem);
     for (int f = 0; f < 4 && !rc; ++f) rc = set_smem_attr((const void*)ks->sweep_fast[f], g.smem);
+    for (int f = 0; f < 4 && !rc; ++f) rc = set_smem_attr((const void*)ks->sweep_fast3[f], g.smem);
     if (rc) return rc;
 
     const size_t S = (size_t)s->stride;
@@ -200,7 +208,8 @@ int mcmcn_run(const mcmcn_model* m, const mcmcn_state* s, const mcmcn_run_args* 
         a.tr_diff = r->trace_diff ? r->trace_diff + it * per_iter : nullptr;
         a.tr_acc = r->trace_accept ? r->trace_accept + it * per_iter : nullptr;
         if (a.tr_ll && !(a.tr_lp && a.tr_diff && a.tr_acc)) { set_error("trace arrays go together"); return MCMCN_ERR_INVALID; }
-        const sweep_fn fn = (fast && !a.use_override) ? ks->sweep_fast[(partial ? MCMCN_F_PARTIAL : 0) | (a.count ? MCMCN_F_COUNT : 0)] : general;
+        const int fidx = (partial ? MCMCN_F_PARTIAL : 0) | (a.count ? MCMCN_F_COUNT : 0);
+        const sweep_fn fn = (fast && !a.use_override) ? (geom3 ? ks->sweep_fast3[fidx] : ks->sweep_fast[fidx]) : general;
         tic(0);
         fn<<<g.grid, g.block, g.smem, stream>>>(a);
         toc();
@@ -259,10 +268,11 @@ int mcmcn_group_loglik(const mcmcn_model* m, const mcmcn_state* s, const double*
     a.pooled_theta = pooled_theta;
     a.out_ll = out_ll;
     const Geometry g = geometry(ks, m, s->n_chains);
+    a.tile_bytes = (int)g.tile_bytes;
     const sweep_fn fn = g.wide ? ks->eval_wide : ks->eval_one;
-    rc = set_smem_attr((const void*)fn, g.smem);
+    rc = set_smem_attr((const void*)fn, g.tile_bytes);
     if (rc) return rc;
-    fn<<<g.grid, g.block, g.smem, (cudaStream_t)stream_>>>(a);
+    fn<<<g.grid, g.block, g.tile_bytes, (cudaStream_t)stream_>>>(a);
     CK(cudaGetLastError());
     return MCMCN_OK;
 }

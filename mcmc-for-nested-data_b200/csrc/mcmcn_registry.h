@@ -14,19 +14,23 @@ struct KernelSet {
     int objective, P, K, precision;
     int c_wide;                 // chains per lane of the wide variant
     sweep_fn sweep_fast[4];     // wide, production: index = MCMCN_F_PARTIAL | MCMCN_F_COUNT
+    sweep_fn sweep_fast3[4];    // same, 128-thread CTAs at 3 per SM (170 registers)
     sweep_fn sweep_wide;        // wide, general (replay tapes, traces, streamed groups)
     sweep_fn sweep_one;         // one chain per lane, general
     sweep_fn eval_wide, eval_one;
     pointwise_fn pointwise;
     int elem_bytes;
+    int park_doubles;           // shared-memory parking slots per chain (6 + Aux doubles)
 };
 
 #define MCMCN_SET(OBJ_ID, OBJ, KK, PREC, T, CW)                                                          \
     {OBJ_ID, OBJ::P, KK, PREC, CW,                                                                       \
      {sweep_kernel<OBJ, CW, T, 2, 0>, sweep_kernel<OBJ, CW, T, 2, 1>, sweep_kernel<OBJ, CW, T, 2, 2>,    \
       sweep_kernel<OBJ, CW, T, 2, 3>},                                                                   \
+     {sweep_kernel<OBJ, CW, T, 3, 0, 128>, sweep_kernel<OBJ, CW, T, 3, 1, 128>,                          \
+      sweep_kernel<OBJ, CW, T, 3, 2, 128>, sweep_kernel<OBJ, CW, T, 3, 3, 128>},                         \
      sweep_kernel<OBJ, CW, T, 2, -1>, sweep_kernel<OBJ, 1, T, 1, -1>,                                    \
-     eval_kernel<OBJ, CW, T>, eval_kernel<OBJ, 1, T>, pointwise_kernel<OBJ, T>, (int)sizeof(T)}
+     eval_kernel<OBJ, CW, T>, eval_kernel<OBJ, 1, T>, pointwise_kernel<OBJ, T>, (int)sizeof(T), 6 + OBJ::AUX_DOUBLES}
 
 const KernelSet* sets_linreg_a(int* n);
 const KernelSet* sets_linreg_b(int* n);
