@@ -220,7 +220,7 @@ def runGpu(args):
         eng.run(w * ips, ips, burn, thin, store=store)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    timing = numpy.zeros(8)
+    timing = numpy.zeros(12)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for k in range(args.steps):
@@ -229,6 +229,7 @@ def runGpu(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if sampler else None
+    eng.collectTiming()            # durations of the launches sampled (every 8th iteration) inside the timed region
 
     # ---- pass 2: same steps through host buffers (H2D of the observation data, D2H of the
     # rows the step retained and of the hyper-parameters), fresh Philox seed
@@ -266,8 +267,7 @@ def runGpu(args):
         chainIters = world * chains * ips * args.steps
         value = chainIters / (ms * 1e-3)
         e2e = chainIters / (msE2e * 1e-3)
-        nSweep = max(timing[3], 1.0)
-        sweepMs = timing[0] / nSweep
+        sweepMs = timing[0] / max(timing[6], 1.0)
         flopsPerLaunch = FLOP_PER_EVAL * P * N * chains
         achieved = flopsPerLaunch / (sweepMs * 1e-3)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
@@ -280,9 +280,10 @@ def runGpu(args):
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h / max(args.steps, 1))},
                 "gpu_launches": int(timing[3] + timing[4] + timing[5]),
-                "kernel_ms": {"step_kernel_avg": sweepMs, "hyper_kernel_avg": timing[1] / max(timing[4], 1.0),
-                              "writeback_avg": timing[2] / max(timing[5], 1.0),
-                              "step_kernel_share": timing[0] / ms},
+                "kernel_ms": {"step_kernel_avg": sweepMs, "hyper_kernel_avg": timing[1] / max(timing[7], 1.0),
+                              "writeback_avg": timing[2] / max(timing[8], 1.0),
+                              "timed_launches": int(timing[6] + timing[7] + timing[8]),
+                              "step_kernel_share": sweepMs * timing[3] / ms},
                 "roofline": {"bound": "fp32", "kernel": "sweep_kernel<LinReg<8>,4,float>",
                              "achieved": achieved / 1e12, "peak": peakFlops / 1e12, "unit": "TFLOP/s",
                              "frac": achieved / peakFlops,
@@ -319,8 +320,9 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=40)
     ap.add_argument("--ref-iters", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--traffic", type=float, default=None,
-                    help="dram bytes per step-kernel launch from the committed ncu capture (profiles/)")
+    ap.add_argument("--traffic", type=float, default=204.2e6,
+                    help="dram__bytes_read.sum + dram__bytes_write.sum per step-kernel launch, from the committed "
+                         "ncu --set full capture (profiles/r1_sweep_kernel_ncu_summary.txt); not measured live")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         print("warning: the timing rules ask for >= 3 warm-up steps", file=sys.stderr)

@@ -149,10 +149,11 @@ typedef struct mcmcn_run_args {
     int32_t use_lprior_override; /* partial pooling: read the current log-prior from state.lprior (iteration iter0 only) */
     int64_t store_row0;          /* row that the first retained iteration of this call goes to */
     int64_t store_rows;          /* capacity in rows */
-    /* optional per-kernel timing (host pointer to 8 doubles, accumulated into; NULL = off):
-     * [0] step-kernel ms, [1] hyper-kernel ms, [2] write-back ms, [3] step launches,
-     * [4] hyper launches, [5] write-back launches.  When set, every launch is bracketed by
-     * CUDA events on `stream` and the call synchronises before returning. */
+    /* optional per-kernel timing (host pointer to 12 doubles that must outlive
+     * mcmcn_timing_collect, accumulated into; NULL = off): [3..5] launches of the step / hyper /
+     * write-back kernels (always counted); every 8th iteration's launches are bracketed by
+     * CUDA events on `stream`, and mcmcn_timing_collect() adds their durations to [0..2] (ms)
+     * and the number of timed launches to [6..8].  The call itself stays asynchronous. */
     double* timing;
 } mcmcn_run_args;
 
@@ -168,6 +169,10 @@ int mcmcn_supported(int objective, int n_params, int n_coef, int precision);
 /* Replaces Sampler._loop + StepMethod.step (posteriorSampling.py:594-613, :862-896). */
 int mcmcn_run(const mcmcn_model* model, const mcmcn_state* state,
               const mcmcn_run_args* args, void* stream);
+
+/* Wait for and read back the events recorded by mcmcn_run calls of this thread that had
+ * `timing` set (see mcmcn_run_args.timing). */
+int mcmcn_timing_collect(void);
 
 /* Group log-likelihood of the current state (posteriorSampling.py:629-635 with
  * proposedParameter=None).  out_ll is device [G][S].  If pooled_theta (device

@@ -13,8 +13,7 @@ typedef void (*pointwise_fn)(const SweepArgs, const long long*, double*);
 struct KernelSet {
     int objective, P, K, precision;
     int c_wide;                 // chains per lane of the wide variant
-    sweep_fn sweep_fast[4];     // wide, production: index = MCMCN_F_PARTIAL | MCMCN_F_COUNT
-    sweep_fn sweep_fast3[4];    // same, 128-thread CTAs at 3 per SM (170 registers)
+    sweep_fn sweep_fast[4];     // wide, production (128-thread CTAs, 3 per SM, 168 registers): index = MCMCN_F_PARTIAL | MCMCN_F_COUNT
     sweep_fn sweep_wide;        // wide, general (replay tapes, traces, streamed groups)
     sweep_fn sweep_one;         // one chain per lane, general
     sweep_fn eval_wide, eval_one;
@@ -25,8 +24,6 @@ struct KernelSet {
 
 #define MCMCN_SET(OBJ_ID, OBJ, KK, PREC, T, CW)                                                          \
     {OBJ_ID, OBJ::P, KK, PREC, CW,                                                                       \
-     {sweep_kernel<OBJ, CW, T, 2, 0>, sweep_kernel<OBJ, CW, T, 2, 1>, sweep_kernel<OBJ, CW, T, 2, 2>,    \
-      sweep_kernel<OBJ, CW, T, 2, 3>},                                                                   \
      {sweep_kernel<OBJ, CW, T, 3, 0, 128>, sweep_kernel<OBJ, CW, T, 3, 1, 128>,                          \
       sweep_kernel<OBJ, CW, T, 3, 2, 128>, sweep_kernel<OBJ, CW, T, 3, 3, 128>},                         \
      sweep_kernel<OBJ, CW, T, 2, -1>, sweep_kernel<OBJ, 1, T, 1, -1>,                                    \

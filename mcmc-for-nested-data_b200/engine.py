@@ -318,6 +318,10 @@ class Engine(object):
             raise RuntimeError("could not find finite group log-likelihoods for every group")
         self._up(self.ll, ll)
 
+    def collectTiming(self):
+        """Wait for the sampled per-kernel events of earlier run(timing=...) calls."""
+        nat.call("mcmcn_timing_collect")
+
     # ------------------------------------------------------------------ run loop
     def run(self, iter0, nIter, burn, thin, store=None, tape=None, trace=False,
             tuneInterval=100, useLpriorOverride=None, timing=None):
@@ -350,7 +354,7 @@ class Engine(object):
         if useLpriorOverride is None:
             useLpriorOverride = self.partial and self.lpriorStale and iter0 == 0
         a.use_lprior_override = 1 if useLpriorOverride else 0
-        if timing is not None:      # numpy float64[8], accumulated into (per-kernel ms and launch counts)
+        if timing is not None:      # numpy float64[12], see mcmcn_run_args.timing; read with collectTiming()
             a.timing = timing.ctypes.data_as(ctypes.c_void_p)
         nat.call("mcmcn_run", ctypes.byref(self.model), ctypes.byref(self.state), ctypes.byref(a), self.stream)
         if iter0 == 0 and nIter > 0:

@@ -83,6 +83,7 @@ PROTOTYPES = {
     "mcmcn_supported": (ctypes.c_int, [ctypes.c_int] * 4),
     "mcmcn_run": (ctypes.c_int, [ctypes.POINTER(Model), ctypes.POINTER(State),
                                  ctypes.POINTER(RunArgs), c_void_p]),
+    "mcmcn_timing_collect": (ctypes.c_int, []),
     "mcmcn_group_loglik": (ctypes.c_int, [ctypes.POINTER(Model), ctypes.POINTER(State),
                                           c_void_p, c_void_p, c_void_p]),
     "mcmcn_pooled_nll": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_void_p, c_void_p, c_void_p]),
