@@ -171,6 +171,15 @@ __device__ __forceinline__ double prior_logpdf(const mcmcn_prior& pr, double x) 
 //   finish        accumulator + Aux -> group log-likelihood
 //   pointwise     one observation's log-likelihood (saveLogLikelihood path)
 
+// Where a block handed to `accumulate` sits: group index, index of its first observation within
+// the group (non-zero when a large group is streamed in chunks), and the group's header in
+// global memory (user objectives).
+struct ObsCtx {
+    int group;
+    int obs0;
+    const void* hdr;
+};
+
 template <typename T> struct Vec4 {};
 template <> struct Vec4<float> {
     __device__ static __forceinline__ void load(const float* p, float (&v)[4]) {
@@ -293,7 +302,7 @@ struct LinReg {
     // FFMA2, FP32 partial sums folded into FP64 every 16 observations.
     template <int C>
     __device__ static __forceinline__ void accumulate(const float* __restrict__ blk, int nobs, const double*,
-                                                      const Work<C, float>& w, double (&acc)[C]) {
+                                                      const Work<C, float>& w, double (&acc)[C], const ObsCtx&) {
         const int nq = (nobs + 3) >> 2;
         for (int q0 = 0; q0 < nq; q0 += 4) {
             f32x2 s2[C];
@@ -327,7 +336,7 @@ struct LinReg {
     // FP64 path (replay verification): same layout, scalar FMAs.
     template <int C>
     __device__ static __forceinline__ void accumulate(const double* __restrict__ blk, int nobs, const double*,
-                                                      const Work<C, double>& w, double (&acc)[C]) {
+                                                      const Work<C, double>& w, double (&acc)[C], const ObsCtx&) {
         const int nq = (nobs + 3) >> 2;
         for (int q = 0; q < nq; ++q) {
             const double* xq = blk + (size_t)q * UNIT;
@@ -366,7 +375,7 @@ struct LinReg {
         return acc * a.mhalf_inv2 - a.rlog;
     }
     template <typename T>
-    __device__ static __forceinline__ double pointwise(const T* __restrict__ blk, int i, const double*, const T (&th)[P]) {
+    __device__ static __forceinline__ double pointwise(const T* __restrict__ blk, int i, const double*, const T (&th)[P], int = 0, const void* = nullptr) {
         const T* xq = blk + (size_t)(i >> 2) * UNIT;
         const int j = i & 3;
         T r = xq[4 * KP + j];
@@ -400,7 +409,7 @@ struct Logit {
 
     template <int C, typename T>
     __device__ static __forceinline__ void accumulate(const T* __restrict__ blk, int nobs, const double*,
-                                                      const Work<C, T>& w, double (&acc)[C]) {
+                                                      const Work<C, T>& w, double (&acc)[C], const ObsCtx&) {
         const int nq = nobs >> 2;
         for (int q = 0; q < nq; ++q) {
             T x4[4], y4[4];
@@ -439,7 +448,7 @@ struct Logit {
     __device__ static __forceinline__ bool aux_depends_on(int) { return false; }
     __device__ static __forceinline__ double finish(double acc, const Aux&) { return acc; }
     template <typename T>
-    __device__ static __forceinline__ double pointwise(const T* __restrict__ blk, int i, const double*, const T (&th)[P]) {
+    __device__ static __forceinline__ double pointwise(const T* __restrict__ blk, int i, const double*, const T (&th)[P], int = 0, const void* = nullptr) {
         const T* xq = blk + (size_t)(i >> 2) * UNIT;
         const T eta = fma_t(th[1], xq[i & 3], th[0]);
         return (double)fma_t(xq[4 + (i & 3)], eta, -softplus_t(eta));
@@ -477,7 +486,7 @@ struct GaussDist {
     }
     template <int C, typename T>
     __device__ static __forceinline__ void accumulate(const T* __restrict__ blk, int nobs, const double* cst,
-                                                      const Work<C, T>& w, double (&acc)[C]) {
+                                                      const Work<C, T>& w, double (&acc)[C], const ObsCtx&) {
         for (int i = 0; i < nobs; ++i) {   // one evaluation per observation, summed in order (:631-633)
             const T* rec = blk + (size_t)(i >> 2) * UNIT + (i & 3) * PP;
 #pragma unroll
@@ -493,10 +502,53 @@ struct GaussDist {
     __device__ static __forceinline__ bool aux_depends_on(int) { return false; }
     __device__ static __forceinline__ double finish(double acc, const Aux&) { return acc; }
     template <typename T>
-    __device__ static __forceinline__ double pointwise(const T* __restrict__ blk, int i, const double* cst, const T (&th)[P]) {
+    __device__ static __forceinline__ double pointwise(const T* __restrict__ blk, int i, const double* cst, const T (&th)[P], int = 0, const void* = nullptr) {
         return (double)row<T>(blk + (size_t)(i >> 2) * UNIT + (i & 3) * PP, cst, th);
     }
 };
+
+// User objective (north star (1), include/mcmcn.h "user objectives"): the NVRTC translation
+// unit defines MCMCN_USER_P / _OBS / _HDR, `mcmc_real`, and the user's
+//   __device__ mcmc_real mcmc_obj_loglik(const mcmc_real* theta, const mcmc_real* obs,
+//                                        const mcmc_real* hdr, int obs_index, int group);
+// before including this header.  Block: [HDR] header, then R records of OBS values.
+#ifdef MCMCN_USER_P
+struct UserObj {
+    static constexpr int P = MCMCN_USER_P;
+    static constexpr int UNIT = MCMCN_USER_OBS;
+    static constexpr int HDR = MCMCN_USER_HDR;
+    static constexpr int OBS_PER_UNIT = 1;
+
+    template <typename T>
+    __device__ static __forceinline__ T local(int, double v, const double*, int) { return (T)v; }
+    template <int C, typename T>
+    struct Work : PlainWork<P, C, T> {};
+
+    template <int C, typename T>
+    __device__ static __forceinline__ void accumulate(const T* __restrict__ blk, int nobs, const double*,
+                                                      const Work<C, T>& w, double (&acc)[C], const ObsCtx& ctx) {
+        const T* hdr = reinterpret_cast<const T*>(ctx.hdr);
+        for (int i = 0; i < nobs; ++i) {
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                acc[c] += (double)mcmc_obj_loglik(w.th[c], blk + (size_t)i * UNIT, hdr, ctx.obs0 + i, ctx.group);
+        }
+    }
+    struct Aux {};
+    static constexpr int AUX_DOUBLES = 0;
+    __device__ static __forceinline__ void aux_put(const Aux&, double*, int) {}
+    __device__ static __forceinline__ Aux aux_get(const double*, int) { return Aux(); }
+    template <int C, typename T>
+    __device__ static __forceinline__ Aux aux(int, const Work<C, T>&, int) { return Aux(); }
+    __device__ static __forceinline__ bool aux_depends_on(int) { return false; }
+    __device__ static __forceinline__ double finish(double acc, const Aux&) { return acc; }
+    template <typename T>
+    __device__ static __forceinline__ double pointwise(const T* __restrict__ blk, int i, const double*, const T (&th)[P],
+                                                       int g, const void* hdr) {
+        return (double)mcmc_obj_loglik(th, blk + (size_t)i * UNIT, reinterpret_cast<const T*>(hdr), i, g);
+    }
+};
+#endif
 
 // ---------------------------------------------------------------- kernel arguments
 struct SweepArgs {
@@ -567,8 +619,12 @@ __device__ __forceinline__ void group_loglik(const SweepArgs& a, const T* blk, T
                                              double (&acc)[C]) {
 #pragma unroll
     for (int c = 0; c < C; ++c) acc[c] = 0.0;
+    ObsCtx ctx;
+    ctx.group = g;
+    ctx.obs0 = 0;
+    ctx.hdr = reinterpret_cast<const T*>(a.data) + a.group_off[g];
     if (!STREAM || blk != nullptr) {
-        Obj::template accumulate<C>(blk + Obj::HDR, R, a.obj_const, w, acc);
+        Obj::template accumulate<C>(blk + Obj::HDR, R, a.obj_const, w, acc, ctx);
     } else {
         const T* src = reinterpret_cast<const T*>(a.data) + a.group_off[g] + Obj::HDR;
         const int unit = Obj::UNIT > 0 ? Obj::UNIT : 1;
@@ -577,7 +633,8 @@ __device__ __forceinline__ void group_loglik(const SweepArgs& a, const T* blk, T
             const int n = min(chunk_obs, R - o);
             const long long elems = (long long)((n + Obj::OBS_PER_UNIT - 1) / Obj::OBS_PER_UNIT) * Obj::UNIT;
             stage_tile<T>(tile, src + (long long)(o / Obj::OBS_PER_UNIT) * Obj::UNIT, elems, mb, parity, true);
-            Obj::template accumulate<C>(tile, n, a.obj_const, w, acc);
+            ctx.obs0 = o;
+            Obj::template accumulate<C>(tile, n, a.obj_const, w, acc, ctx);
         }
     }
 }
@@ -873,7 +930,7 @@ __global__ void pointwise_kernel(const SweepArgs a, const long long* obs_off, do
     const int R = a.group_nobs[g];
     const long long o0 = obs_off[g];
     for (int i = 0; i < R; ++i)
-        out[(size_t)(o0 + i) * S + ch] = Obj::template pointwise<T>(blk + Obj::HDR, i, a.obj_const, th);
+        out[(size_t)(o0 + i) * S + ch] = Obj::template pointwise<T>(blk + Obj::HDR, i, a.obj_const, th, g, blk);
 }
 
 // ---------------------------------------------------------------- Gibbs hyper update

@@ -30,6 +30,14 @@ struct Stamp { cudaEvent_t e0, e1; int kind; double* out; };
 static thread_local std::vector<Stamp> g_stamps;
 
 // ---------------------------------------------------------------- kernel registry
+const KernelSet* user_kernel_set(const void* handle);   // mcmcn_nvrtc.cu
+
+// AOT kernels (host stubs) and NVRTC kernels (cudaKernel_t handles) launch the same way
+static cudaError_t launch_sweep(sweep_fn fn, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, SweepArgs& a) {
+    void* args[] = {&a};
+    return cudaLaunchKernel((const void*)fn, grid, block, args, smem, stream);
+}
+
 static const KernelSet* find_set(int objective, int P, int K, int precision) {
     typedef const KernelSet* (*getter)(int*);
     static const getter getters[] = {sets_linreg_a, sets_linreg_b, sets_linreg_c, sets_logit, sets_gauss};
@@ -113,7 +121,16 @@ static int validate(const mcmcn_model* m, const mcmcn_state* s, const KernelSet*
     if (m->n_groups < 1 || m->n_tasks < 1) { set_error("empty model"); return MCMCN_ERR_INVALID; }
     if (s->n_chains < 1 || s->stride < s->n_chains || (s->stride & 31)) { set_error("bad chain count/stride %d/%d", s->n_chains, s->stride); return MCMCN_ERR_INVALID; }
     if (!m->task_group0_host || !m->group_off_host) { set_error("host task tables missing"); return MCMCN_ERR_INVALID; }
-    *ks = find_set(m->objective, m->n_params, m->n_coef, m->precision);
+    if (m->objective == MCMCN_OBJ_USER) {
+        *ks = user_kernel_set(m->user_objective);
+        if (*ks && ((*ks)->P != m->n_params || (*ks)->precision != m->precision)) {
+            set_error("user objective was compiled for P=%d precision=%d, model has P=%d precision=%d", (*ks)->P,
+                      (*ks)->precision, m->n_params, m->precision);
+            return MCMCN_ERR_INVALID;
+        }
+    } else {
+        *ks = find_set(m->objective, m->n_params, m->n_coef, m->precision);
+    }
     if (!*ks) {
         set_error("objective %d with P=%d K=%d precision=%d is not compiled in", m->objective, m->n_params, m->n_coef, m->precision);
         return MCMCN_ERR_UNSUPPORTED;
@@ -215,7 +232,7 @@ int mcmcn_run(const mcmcn_model* m, const mcmcn_state* s, const mcmcn_run_args* 
         const int fidx = (partial ? MCMCN_F_PARTIAL : 0) | (a.count ? MCMCN_F_COUNT : 0);
         const sweep_fn fn = (fast && !a.use_override) ? ks->sweep_fast[fidx] : general;
         tic(0);
-        fn<<<g.grid, g.block, g.smem, stream>>>(a);
+        CK(launch_sweep(fn, g.grid, g.block, g.smem, stream, a));
         toc();
 
         if (partial) {
@@ -280,7 +297,7 @@ int mcmcn_group_loglik(const mcmcn_model* m, const mcmcn_state* s, const double*
     const sweep_fn fn = g.wide ? ks->eval_wide : ks->eval_one;
     rc = set_smem_attr((const void*)fn, g.tile_bytes);
     if (rc) return rc;
-    fn<<<g.grid, g.block, g.tile_bytes, (cudaStream_t)stream_>>>(a);
+    CK(launch_sweep(fn, g.grid, g.block, g.tile_bytes, (cudaStream_t)stream_, a));
     CK(cudaGetLastError());
     return MCMCN_OK;
 }
@@ -314,8 +331,11 @@ int mcmcn_pointwise_loglik(const mcmcn_model* m, const mcmcn_state* s, double* o
     delete[] nobs_h;
     if (e != cudaSuccess) { cudaFree(obs_off_d); set_error("cuda: %s", cudaGetErrorString(e)); return MCMCN_ERR_CUDA; }
     const dim3 grid((unsigned)G, (unsigned)((s->n_chains + 127) / 128), 1);
-    ks->pointwise<<<grid, 128, 0, (cudaStream_t)stream_>>>(a, obs_off_d, out);
-    e = cudaStreamSynchronize((cudaStream_t)stream_);
+    {
+        void* args[] = {&a, &obs_off_d, &out};
+        e = cudaLaunchKernel((const void*)ks->pointwise, grid, dim3(128, 1, 1), args, 0, (cudaStream_t)stream_);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream_);
     cudaFree(obs_off_d);
     if (e != cudaSuccess) { set_error("cuda: %s", cudaGetErrorString(e)); return MCMCN_ERR_CUDA; }
     return MCMCN_OK;

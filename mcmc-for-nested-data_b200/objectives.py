@@ -79,6 +79,46 @@ class Objective(object):
         self.nObservations = int(len(self.groupOfObservation))
         return self
 
+    @classmethod
+    def from_source(cls, source, nParameters, records, header=None, precision="fp32"):
+        """A user objective compiled by NVRTC (north star (1); C ABI in include/mcmcn.h).
+
+        ``source`` is CUDA C++ defining
+
+            __device__ mcmc_real mcmc_obj_loglik(const mcmc_real* theta, const mcmc_real* obs,
+                                                 const mcmc_real* hdr, int obs_index, int group);
+
+        returning the pointwise log-likelihood of one observation given its own group's
+        ``nParameters`` values (the reference's contract, posteriorSampling.py:61-102: ll[i] may
+        depend only on observation i and its group's parameters).  ``records`` is [N][F]: the
+        per-observation values the function reads through ``obs`` (F is padded to a multiple of 4);
+        ``header`` is an optional [G][H] array of per-group constants read through ``hdr``.
+        ``mcmc_real`` is float ("fp32") or double ("fp64")."""
+        import ctypes
+        records = numpy.ascontiguousarray(records, dtype=numpy.float64)
+        if records.ndim != 2:
+            raise ValueError("records must be [N][F]")
+        self = cls(nat.OBJ_USER, nParameters, precision)
+        self.records = records
+        self.header = None if header is None else numpy.ascontiguousarray(header, dtype=numpy.float64)
+        self.obsFloats = _round4(records.shape[1])
+        self.hdrFloats = 0 if header is None else _round4(self.header.shape[1])
+        self.nObservations = records.shape[0]
+        self.source = source
+        handle = ctypes.c_void_p()
+        nat.call("mcmcn_user_objective_compile", source.encode("utf-8"), self.nParameters, self.obsFloats,
+                 self.hdrFloats, 32 if precision == "fp32" else 64, ctypes.byref(handle))
+        self.userHandle = handle
+        return self
+
+    def __del__(self):
+        try:
+            if getattr(self, "userHandle", None):
+                nat.load().mcmcn_user_objective_free(self.userHandle)
+                self.userHandle = None
+        except Exception:
+            pass
+
     # ------------------------------------------------------------ packing
     @property
     def elementDtype(self):
@@ -94,6 +134,24 @@ class Objective(object):
             raise ValueError("nResponsesPerGroup sums to %d but the objective holds %d observations"
                              % (sum(nResp), self.nObservations))
         dt = self.elementDtype
+        if self.kind == nat.OBJ_USER:
+            if self.header is not None and self.header.shape[0] != len(nResp):
+                raise ValueError("a per-group header cannot be used with %d stepped groups (complete pooling "
+                                 "makes one group of all observations)" % len(nResp))
+            F, H = self.obsFloats, self.hdrFloats
+            sizes = numpy.array([H + r * F for r in nResp], dtype=numpy.int64)
+            group_off = numpy.zeros(len(nResp) + 1, dtype=numpy.int64)
+            group_off[1:] = numpy.cumsum(sizes)
+            data = numpy.zeros(int(group_off[-1]), dtype=dt)
+            start = 0
+            for g, r in enumerate(nResp):
+                blk = data[group_off[g]:group_off[g + 1]]
+                if H:
+                    blk[:self.header.shape[1]] = self.header[g]
+                rec = blk[H:].reshape(r, F)
+                rec[:, :self.records.shape[1]] = self.records[start:start + r]
+                start += r
+            return data, group_off, numpy.array(nResp, dtype=numpy.int32), None
         if self.kind == nat.OBJ_LINEAR_REGRESSION:
             K, KP = self.nCoef, _round4(self.nCoef)
             unit = 4 * KP + 4
