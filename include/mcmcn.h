@@ -106,6 +106,16 @@ typedef struct mcmcn_model {
     const double* obj_const;     /* device objective constants (gaussian_distribution: sd[P], log sd[P];
                                     linear_regression: bbar[G][K]) */
     const void* user_objective;  /* handle from mcmcn_user_objective_compile, or NULL */
+    /* Tensor-core operand blocks (linear_regression, precision 32, K <= 8; NULL = not provided, the
+     * FP32-pipe kernel is used).  Block of group g at float offset tc_group_off[g]: three slabs of
+     * [Np][8] floats, Np = R rounded up to 16 (at least 16): X_hi, X_lo, NE, where x = x_hi + x_lo
+     * with both parts rounded to TF32, and NE row n = (ne_hi, ne_mid, ne_lo, 0, 0, 0, 0, 0) with
+     * ne = ne_hi + ne_mid + ne_lo exactly.  Within a slab element (n, k) sits at float index
+     * (n/8)*64 + (k/4)*32 + (n%8)*4 + (k%4): the K-major, no-swizzle shared-memory layout that
+     * tcgen05.mma reads (8-row x 16-byte core matrices).  Padding rows and coefficients are zero. */
+    const void* tc_data;             /* device float */
+    const int64_t* tc_group_off;     /* device [G+1], in floats */
+    int64_t tc_max_block_floats;     /* largest block */
     mcmcn_prior prior[MCMCN_MAX_PARAMS];   /* none / complete pooling only */
 } mcmcn_model;
 

@@ -586,6 +586,10 @@ struct SweepArgs {
     // eval-only mode
     const double* pooled_theta;   // [P][S] or NULL
     double* out_ll;               // [G][S]
+    // tensor-core path (mcmcn_tc.cuh): per-group blocks [X_hi | X_lo | NE], element offsets, stage size
+    const void* tc_data;
+    const long long* tc_group_off;
+    int tc_stage_bytes;
 };
 
 // Compile-time specialisation of the step kernel.  F < 0: everything decided at run time (the

@@ -25,6 +25,11 @@ void set_error(const char* fmt, ...) {
 }
 
 static const int kTileCapBytes = 64 * 1024;
+// tcgen05 path (mcmcn_tc.cuh): two TMA stages of one group block each + the 4 KB ones operand; the
+// floor keeps the CTAs at four per SM, which is what their 128 TMEM columns allow
+static const int kTcStageCapBytes = 24 * 1024;
+static const int kTcSmemFloorBytes = 48 * 1024;
+static const int kTcCtaSlots = 4 * 148;
 
 struct Stamp { cudaEvent_t e0, e1; int kind; double* out; };
 static thread_local std::vector<Stamp> g_stamps;
@@ -112,7 +117,39 @@ static int fill_args(SweepArgs& a, const KernelSet* ks, const mcmcn_model* m, co
     a.ll = s->ll;
     a.lprior = s->lprior;
     a.hyper = s->hyper;
+    a.tc_data = m->tc_data;
+    a.tc_group_off = reinterpret_cast<const long long*>(m->tc_group_off);
     return MCMCN_OK;
+}
+
+// Tensor-core launch shape: blockIdx.y = block of 128 chains, blockIdx.x = contiguous range of
+// groups.  Ranges are sized so that the grid is a whole number of 2-CTA-per-SM waves when it is
+// small and at most 32 groups long when it is large.
+static bool tc_eligible(const mcmcn_model* m) {
+    return m->objective == MCMCN_OBJ_LINEAR_REGRESSION && m->precision == 32 && m->n_coef <= 8 && m->tc_data &&
+           m->tc_group_off && m->tc_max_block_floats > 0 && m->tc_max_block_floats * 4 <= kTcStageCapBytes &&
+           !getenv("MCMCN_NO_TC");
+}
+static Geometry tc_geometry(const mcmcn_model* m, int n_chains, int* stage_bytes) {
+    Geometry g;
+    const int ncb = (n_chains + 127) / 128;
+    const long long tasks = (long long)ncb * m->n_groups;
+    int nr = m->n_groups;
+    if (tasks > kTcCtaSlots) {
+        const long long waves = (tasks + (long long)kTcCtaSlots * 32 - 1) / ((long long)kTcCtaSlots * 32);
+        long long r = (waves * kTcCtaSlots + ncb / 2) / ncb;
+        if (r < 1) r = 1;
+        if (r > m->n_groups) r = m->n_groups;
+        nr = (int)r;
+    }
+    g.wide = true; g.all_fit = true; g.C = 1; g.nw = 4;
+    g.grid = dim3((unsigned)nr, (unsigned)ncb, 1);
+    g.block = dim3(128, 1, 1);
+    *stage_bytes = (int)((m->tc_max_block_floats * 4 + 1023) & ~1023LL);
+    size_t smem = 2 * (size_t)*stage_bytes + 4096 + 1024;
+    if (smem < (size_t)kTcSmemFloorBytes) smem = kTcSmemFloorBytes;
+    g.tile_bytes = g.smem = smem;
+    return g;
 }
 
 static int validate(const mcmcn_model* m, const mcmcn_state* s, const KernelSet** ks) {
@@ -139,7 +176,7 @@ static int validate(const mcmcn_model* m, const mcmcn_state* s, const KernelSet*
 }
 
 static int set_smem_attr(const void* fn, size_t smem) {
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 40 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return MCMCN_OK;
 }
 
@@ -175,19 +212,24 @@ int mcmcn_run(const mcmcn_model* m, const mcmcn_state* s, const mcmcn_run_args* 
     // geometry: 128-thread CTAs (4 warps = 512 chains of one group), 3 per SM at 168 registers, which
     // keeps the observation loop spill-free (measured: 1.26 M chain-it/s against 1.15 M for 4 CTAs at
     // 128 registers and 1.10 M for 2 CTAs at 254)
-    const Geometry g = geometry(ks, m, s->n_chains, 4);
+    const bool tc = tc_eligible(m);
+    int tc_stage_bytes = 0;
+    const Geometry g = tc ? tc_geometry(m, s->n_chains, &tc_stage_bytes) : geometry(ks, m, s->n_chains, 4);
+    a.tc_stage_bytes = tc_stage_bytes;
     // production variants (pooling mode and burn-in bookkeeping folded at compile time) when
     // there is no tape, no trace and every task fits the tile; the general kernel otherwise
     a.tile_bytes = (int)g.tile_bytes;
     const bool fast = g.wide && g.all_fit && !r->tape_z && !r->trace_ll && !r->tape_accept &&
                       !getenv("MCMCN_GENERAL");   // (the log-prior override iteration also runs general)
     if (getenv("MCMCN_DEBUG"))
-        fprintf(stderr, "mcmcn_run: fast=%d wide=%d all_fit=%d tape=%p trace=%p force=%p override=%d partial=%d smem=%zu grid=(%u,%u) block=%u\n",
-                (int)fast, (int)g.wide, (int)g.all_fit, (const void*)r->tape_z, (void*)r->trace_ll, (const void*)r->tape_accept,
+        fprintf(stderr, "mcmcn_run: tc=%d fast=%d wide=%d all_fit=%d tape=%p trace=%p force=%p override=%d partial=%d smem=%zu grid=(%u,%u) block=%u\n",
+                (int)tc, (int)fast, (int)g.wide, (int)g.all_fit, (const void*)r->tape_z, (void*)r->trace_ll, (const void*)r->tape_accept,
                 r->use_lprior_override, (int)partial, g.smem, g.grid.x, g.grid.y, g.block.x);
-    const sweep_fn general = g.wide ? ks->sweep_wide : ks->sweep_one;
+    const sweep_fn general = tc ? tc_sweep_kernel(-1) : (g.wide ? ks->sweep_wide : ks->sweep_one);
+    sweep_fn fast_fn[4];
+    for (int f = 0; f < 4; ++f) fast_fn[f] = tc ? tc_sweep_kernel(f) : ks->sweep_fast[f];
     rc = set_smem_attr((const void*)general, g.smem);
-    for (int f = 0; f < 4 && !rc; ++f) rc = set_smem_attr((const void*)ks->sweep_fast[f], g.smem);
+    for (int f = 0; f < 4 && !rc; ++f) rc = set_smem_attr((const void*)fast_fn[f], g.smem);
     if (rc) return rc;
 
     const size_t S = (size_t)s->stride;
@@ -230,7 +272,7 @@ int mcmcn_run(const mcmcn_model* m, const mcmcn_state* s, const mcmcn_run_args* 
         a.tr_acc = r->trace_accept ? r->trace_accept + it * per_iter : nullptr;
         if (a.tr_ll && !(a.tr_lp && a.tr_diff && a.tr_acc)) { set_error("trace arrays go together"); return MCMCN_ERR_INVALID; }
         const int fidx = (partial ? MCMCN_F_PARTIAL : 0) | (a.count ? MCMCN_F_COUNT : 0);
-        const sweep_fn fn = (fast && !a.use_override) ? ks->sweep_fast[fidx] : general;
+        const sweep_fn fn = (fast && !a.use_override) ? fast_fn[fidx] : general;
         tic(0);
         CK(launch_sweep(fn, g.grid, g.block, g.smem, stream, a));
         toc();

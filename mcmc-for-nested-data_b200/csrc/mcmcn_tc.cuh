@@ -1,0 +1,424 @@
+// mcmcn_tc.cuh -- tcgen05 step kernel for the linear-regression objective (north star (2):
+// "the regression linear predictor X.B, batched over chains, is the only dense contraction").
+//
+// Same algorithm, update order and decision tree as sweep_kernel (mcmcn_device.cuh; reference
+// posteriorSampling.py:594-613, :334-383); only the evaluation of the group log-likelihood
+// moves.  For one group and 128 chains the residuals of all observations are one small GEMM
+//
+//     D[chain][obs] = sum_k A[chain][k] * Xt[k][obs]        M = 128 chains, N = obs, K = 8
+//
+// issued as tcgen05.mma kind::tf32 with the accumulator in tensor memory.  FP32 accuracy comes
+// from the 3xTF32 split (a = a_hi + a_lo, x = x_hi + x_lo, each part exactly representable in
+// TF32): D = A_hi.X_hi + A_lo.X_hi + A_hi.X_lo, plus a fourth MMA that adds the centred
+// response ne = x.bbar - y as 1 * (ne_hi + ne_mid + ne_lo), so the accumulator holds the
+// residual itself (measured against FP64: 5e-7 of the largest residual, tools/tc_probe.cu).
+//
+//   * lanes = chains: thread t of the CTA owns TMEM lane t.  It writes its chain's
+//     coefficients (A operand, tcgen05.st) and reads back its chain's row of residuals
+//     (tcgen05.ld), squares and sums them with packed FFMA2 -- no cross-thread reduction.
+//   * B operand: the group's observation block [X_hi | X_lo | NE], K-major, no swizzle, staged
+//     in shared memory by one TMA bulk copy, double-buffered over groups.
+//   * accumulator: 112 columns (observations) at a time; the chain state and random numbers of
+//     the NEXT sweep are fetched while the MMAs of this sweep run.  Only column p of the A
+//     operand changes per sweep (two one-column tcgen05.st).
+//   * 128 TMEM columns per CTA (accumulator 112 + A_hi 8 + A_lo 8; the constant ones operand
+//     of the ne MMA lives in shared memory) -> four CTAs per SM: the decision code is a chain of
+//     dependent FP64 / Philox instructions, and it is the other CTAs' warps that hide it.
+#pragma once
+
+#include "mcmcn_device.cuh"
+
+namespace mcmcn {
+
+// ---------------------------------------------------------------- tcgen05 / TMEM PTX
+__device__ __forceinline__ void tmem_alloc(unsigned* slot, unsigned ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_free(unsigned addr, unsigned ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 16 consecutive columns of this thread's lane
+__device__ __forceinline__ void tmem_ld16(unsigned addr, unsigned (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(addr));
+}
+// tcgen05.wait::ld that also carries the loaded registers, so no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_wait_ld(unsigned (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :: "memory");
+}
+__device__ __forceinline__ void tmem_st8(unsigned addr, const unsigned (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(addr), "r"(v[0]),
+                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void mma_commit(unsigned mb) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mb) : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem descriptor], kind::tf32, one CTA
+__device__ __forceinline__ void mma_tf32_ts(unsigned d, unsigned a, unsigned long long bdesc, unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d), "r"(a),
+        "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Shared-memory matrix descriptor, K-major, no swizzle: 8-row x 16-byte core matrices; the two
+// 16-byte halves of K = 8 TF32 values are `lbo` bytes apart, consecutive 8-row groups `sbo` bytes.
+__device__ __forceinline__ unsigned long long tc_smem_desc(unsigned addr, unsigned lbo, unsigned sbo) {
+    return (unsigned long long)((addr >> 4) & 0x3FFF) | ((unsigned long long)((lbo >> 4) & 0x3FFF) << 16) |
+           ((unsigned long long)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// Instruction descriptor: D = F32, A = B = TF32, both K-major, dense
+__device__ __forceinline__ unsigned tc_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
+}
+// nearest TF32 (10 explicit mantissa bits) of an FP32 value, as bits
+__device__ __forceinline__ unsigned tf32_rn(float v) { return (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u; }
+
+// TMEM column map of one CTA: 128 columns -> four CTAs per SM
+#define MCMCN_TC_CH 112        /* observations (columns) of the accumulator */
+#define MCMCN_TC_D 0
+#define MCMCN_TC_A_HI 112
+#define MCMCN_TC_A_LO 120
+#define MCMCN_TC_COLS 128
+#define MCMCN_TC_THREADS 128
+#define MCMCN_TC_ONES_BYTES 4096   /* [128][8] constant A operand of the ne MMA, in shared memory */
+
+__device__ __forceinline__ void tmem_st1(unsigned addr, unsigned v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(addr), "r"(v) : "memory");
+}
+// D[tmem] (+)= A[smem descriptor] . B[smem descriptor], kind::tf32, one CTA
+__device__ __forceinline__ void mma_tf32_ss(unsigned d, unsigned long long adesc, unsigned long long bdesc, unsigned idesc,
+                                            unsigned accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(adesc),
+        "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// The 4 MMAs of observation chunk c of the block staged at `stage` (shared-memory address);
+// completion is signalled on `mbar`.
+__device__ __forceinline__ void tc_issue_chunk(unsigned tbase, unsigned stage, unsigned ones, int np, int c, unsigned mbar) {
+    const int row0 = c * MCMCN_TC_CH;
+    const int nc = min(MCMCN_TC_CH, np - row0);
+    const unsigned idesc = tc_idesc(128, nc);
+    const unsigned slab = (unsigned)np * 32u;
+    const unsigned base = stage + (unsigned)row0 * 32u;
+    const unsigned d = tbase + MCMCN_TC_D;
+    mma_tf32_ts(d, tbase + MCMCN_TC_A_HI, tc_smem_desc(base, 128, 256), idesc, 0);               // A_hi . X_hi
+    mma_tf32_ts(d, tbase + MCMCN_TC_A_LO, tc_smem_desc(base, 128, 256), idesc, 1);               // A_lo . X_hi
+    mma_tf32_ts(d, tbase + MCMCN_TC_A_HI, tc_smem_desc(base + slab, 128, 256), idesc, 1);        // A_hi . X_lo
+    mma_tf32_ss(d, tc_smem_desc(ones, 128, 256), tc_smem_desc(base + 2 * slab, 128, 256), idesc, 1);   // 1 . (ne_hi, ne_mid, ne_lo)
+    mma_commit(mbar);
+}
+
+#define MCMCN_TC_CONSUME(v, s)                                                    \
+    _Pragma("unroll") for (int k = 0; k < 8; ++k) {                               \
+        f32x2 r;                                                                  \
+        asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(v[2 * k]), "r"(v[2 * k + 1])); \
+        s[k & 3] = ffma2(r, r, s[k & 3]);                                         \
+    }
+
+// Sum of squares of PIECES x 16 accumulator columns of this thread's lane, fully unrolled: the
+// load of piece j + 1 is in flight while piece j is squared (FFMA2, four FP32 pair accumulators).
+template <int PIECES>
+__device__ __forceinline__ double tc_sum_squares_fixed(unsigned addr) {
+    f32x2 s[4] = {0ull, 0ull, 0ull, 0ull};
+    unsigned v[2][16];
+    tmem_ld16(addr, v[0]);
+    tmem_wait_ld(v[0]);
+#pragma unroll
+    for (int j = 0; j < PIECES; ++j) {
+        if (j + 1 < PIECES) tmem_ld16(addr + 16 * (j + 1), v[(j + 1) & 1]);
+        MCMCN_TC_CONSUME(v[j & 1], s)
+        if (j + 1 < PIECES) tmem_wait_ld(v[(j + 1) & 1]);
+    }
+    return (double)((sum2(s[0]) + sum2(s[1])) + (sum2(s[2]) + sum2(s[3])));
+}
+__device__ __forceinline__ double tc_sum_squares_any(unsigned addr, int pieces) {
+    f32x2 s[4] = {0ull, 0ull, 0ull, 0ull};
+    unsigned va[16];
+    for (int j = 0; j < pieces; ++j) {
+        tmem_ld16(addr + 16 * j, va);
+        tmem_wait_ld(va);
+        MCMCN_TC_CONSUME(va, s)
+    }
+    return (double)((sum2(s[0]) + sum2(s[1])) + (sum2(s[2]) + sum2(s[3])));
+}
+__device__ __forceinline__ double tc_sum_squares(unsigned addr, int pieces) {
+    switch (pieces) {
+        case 7: return tc_sum_squares_fixed<7>(addr);
+        case 6: return tc_sum_squares_fixed<6>(addr);
+        default: return tc_sum_squares_any(addr, pieces);
+    }
+}
+
+// What a sweep reads from the chain state and the random stream; none of it depends on the
+// decisions of earlier sweeps of the same iteration, so it is fetched one sweep ahead.
+struct TcInputs {
+    double cur, sc, z, u;
+    double h_mu, h_lsd, h_isd;      // partial pooling: this name's hyper-parameters
+    double lp_cur;                  // fixed priors / log-prior override: stored log-prior of the current value
+};
+
+template <bool GENERAL>
+__device__ __forceinline__ TcInputs tc_fetch(const SweepArgs& a, int p, int g, int chl, bool partial, bool replay, bool override_lp) {
+    const int P = a.P;
+    const size_t S = (size_t)a.S;
+    const size_t row = ((size_t)p * a.G + g) * S;
+    TcInputs o;
+    o.cur = a.theta[row + chl];
+    o.sc = a.scale[row + chl];
+    o.h_mu = o.h_lsd = o.h_isd = o.lp_cur = 0.0;
+    if (partial) {
+        o.h_mu = a.hyper[((size_t)0 * P + p) * S + chl];
+        o.h_lsd = a.hyper[((size_t)3 * P + p) * S + chl];
+        o.h_isd = a.hyper[((size_t)4 * P + p) * S + chl];
+        if (GENERAL && override_lp) o.lp_cur = a.lprior[row + chl];
+    } else {
+        o.lp_cur = a.lprior[row + chl];
+    }
+    if (GENERAL && replay) {
+        o.z = a.tape_z[row + chl];
+        o.u = a.tape_u[row + chl];
+    } else {
+        const uint4 rnd = philox_draw(a.chain_id0 + chl, a.seed, a.iter, MCMCN_STREAM_SWEEP, (unsigned)(p * a.G + g), 0u);
+        o.z = normal_from(rnd.x, rnd.y);
+        o.u = uniform_from(rnd.z, rnd.w);
+    }
+    return o;
+}
+
+// grid = (group ranges, chain blocks of 128); block = 128 threads; dynamic shared memory =
+// the constant ones operand + 2 stages of a.tc_stage_bytes (1024-byte aligned).
+template <int F>
+__global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const SweepArgs a) {
+    constexpr bool GENERAL = F < 0;
+    const bool partial = GENERAL ? (a.partial != 0) : ((F & MCMCN_F_PARTIAL) != 0);
+    const bool count = GENERAL ? (a.count != 0) : ((F & MCMCN_F_COUNT) != 0);
+    const bool replay = GENERAL && a.tape_z != nullptr;
+    const bool trace = GENERAL && a.tr_ll != nullptr;
+    const bool forced = GENERAL && a.tape_acc != nullptr;
+    const bool override_lp = GENERAL && a.use_override != 0;
+    const int P = a.P, K = a.P - 1;
+
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ unsigned long long mbar_s[3];          // [0..1] TMA stage full, [2] accumulator full
+    __shared__ unsigned tmem_base_s;
+
+    const int nr = gridDim.x;
+    const int g0 = (int)(((long long)a.G * blockIdx.x) / nr), g1 = (int)(((long long)a.G * (blockIdx.x + 1)) / nr);
+    if (g0 >= g1) return;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const unsigned ones = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const unsigned stage0 = ones + MCMCN_TC_ONES_BYTES;
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&mbar_s[i]), 1);
+    }
+    {   // constant A operand of the ne MMA: every row (1, 1, 1, 0 | 0, 0, 0, 0), K-major core matrices
+        const float4 lo4 = make_float4(1.0f, 1.0f, 1.0f, 0.0f), z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        for (int i = tid; i < MCMCN_TC_ONES_BYTES / 16; i += MCMCN_TC_THREADS) {
+            const bool first_half = ((i >> 3) & 1) == 0;               // 8 rows x 16 bytes per K half
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ones + 16u * i), "f"(first_half ? lo4.x : z4.x),
+                         "f"(first_half ? lo4.y : z4.y), "f"(first_half ? lo4.z : z4.z), "f"(z4.w) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor core reads
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_s, MCMCN_TC_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tbase = tmem_base_s;
+    const unsigned tlane = tbase + ((unsigned)warp << 21);             // lane field = 32 * warp
+    const unsigned mb_tma0 = smem_u32(&mbar_s[0]), mb_mma = smem_u32(&mbar_s[2]);
+
+    const float* tc = reinterpret_cast<const float*>(a.tc_data);
+    auto stage_group = [&](int s, int g) {                             // thread 0 only
+        const long long e0 = a.tc_group_off[g], e1 = a.tc_group_off[g + 1];
+        const unsigned bytes = (unsigned)((e1 - e0) * 4);
+        mbar_expect_tx(mb_tma0 + 8u * s, bytes);
+        tma_bulk_g2s(stage0 + (unsigned)s * (unsigned)a.tc_stage_bytes, tc + e0, bytes, mb_tma0 + 8u * s);
+    };
+    if (tid == 0) {
+        stage_group(0, g0);
+        if (g0 + 1 < g1) stage_group(1, g0 + 1);
+    }
+
+    const int ch = blockIdx.y * MCMCN_TC_THREADS + tid;
+    const bool on = ch < a.n_chains;
+    const int chl = min(ch, a.n_chains - 1);                           // lanes past the last chain redo its work, store nothing
+    const size_t S = (size_t)a.S;
+    unsigned tma_phase = 0, mma_phase = 0;
+
+    for (int g = g0; g < g1; ++g) {
+        const int s = (g - g0) & 1;
+        const int R = a.group_nobs[g];
+        const int np = max(16, (R + 15) & ~15);                        // padded observation count of the block
+        const int nchunks = (np + MCMCN_TC_CH - 1) / MCMCN_TC_CH;
+        const unsigned stage = stage0 + (unsigned)s * (unsigned)a.tc_stage_bytes;
+        const double* bbar = a.obj_const + (size_t)g * K;
+
+        TcInputs in = tc_fetch<GENERAL>(a, 0, g, chl, partial, replay, override_lp);
+        {   // A operand of the current state: centred coefficients (FP32), split hi / lo
+            unsigned hi[8], lo[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float b = k < K ? (float)__dsub_rn(a.theta[((size_t)k * a.G + g) * S + chl], bbar[k]) : 0.0f;
+                hi[k] = tf32_rn(b);
+                lo[k] = tf32_rn(b - __uint_as_float(hi[k]));
+            }
+            tmem_st8(tlane + MCMCN_TC_A_HI, hi);
+            tmem_st8(tlane + MCMCN_TC_A_LO, lo);
+        }
+        double aux_m, aux_r;                                           // LinReg::Aux of the current sigma
+        {
+            const double sg = (double)(float)a.theta[((size_t)K * a.G + g) * S + chl];
+            if (!(sg > 0.0)) {
+                aux_m = aux_r = __longlong_as_double(0x7ff8000000000000LL);
+            } else {
+                const double inv = 1.0 / sg;
+                aux_m = -0.5 * inv * inv;
+                aux_r = (double)R * (log(sg) + MCMCN_LOG_SQRT_2PI);
+            }
+        }
+        double ll_cur = a.ll[(size_t)g * S + chl];
+        mbar_wait(mb_tma0 + 8u * s, (tma_phase >> s) & 1u);
+        tma_phase ^= 1u << s;
+
+#pragma unroll 1
+        for (int p = 0; p < P; ++p) {
+            const size_t at = ((size_t)p * a.G + g) * S + chl;
+            const bool is_sigma = p == K;
+            // proposal and log-priors (pure functions of state known before the sweep)
+            const double prop = __dadd_rn(in.cur, __dmul_rn(in.sc, in.z));     // numpy.random.normal(value, sd), :304-306
+            double lp_prop, lp_cur;
+            if (partial) {
+                lp_prop = norm_logpdf_inv(prop, in.h_mu, in.h_isd, in.h_lsd);
+                lp_cur = (GENERAL && override_lp) ? in.lp_cur : norm_logpdf_inv(in.cur, in.h_mu, in.h_isd, in.h_lsd);
+            } else {
+                lp_prop = prior_logpdf(a.prior[p], prop);
+                lp_cur = in.lp_cur;
+            }
+            const double u = in.u;
+            double m_prop = aux_m, r_prop = aux_r;
+            float wcur = 0.0f, wprop = 0.0f;
+            if (is_sigma) {                                            // LinReg::aux of the proposed sigma
+                const double sg = (double)(float)prop;
+                if (!(sg > 0.0)) {                                     // scipy: scale <= 0 -> nan
+                    m_prop = r_prop = __longlong_as_double(0x7ff8000000000000LL);
+                } else {
+                    const double inv = 1.0 / sg;
+                    m_prop = -0.5 * inv * inv;
+                    r_prop = (double)R * (log(sg) + MCMCN_LOG_SQRT_2PI);
+                }
+            } else {                                                   // column p of the A operand <- the proposal
+                wcur = (float)__dsub_rn(in.cur, bbar[p]);
+                wprop = (float)__dsub_rn(prop, bbar[p]);
+                const unsigned h = tf32_rn(wprop);
+                tmem_st1(tlane + MCMCN_TC_A_HI + p, h);
+                tmem_st1(tlane + MCMCN_TC_A_LO + p, tf32_rn(wprop - __uint_as_float(h)));
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                tc_issue_chunk(tbase, stage, ones, np, 0, mb_mma);
+            }
+            // while the tensor core works: state and random numbers of the next sweep
+            if (p + 1 < P) in = tc_fetch<GENERAL>(a, p + 1, g, chl, partial, replay, override_lp);
+
+            double acc = 0.0;
+            for (int c = 0; c < nchunks; ++c) {
+                mbar_wait(mb_mma, mma_phase);
+                mma_phase ^= 1u;
+                tc_fence_after();
+                const int nc = min(MCMCN_TC_CH, np - c * MCMCN_TC_CH);
+                acc += tc_sum_squares(tlane + MCMCN_TC_D, nc >> 4);
+                if (c + 1 < nchunks) {                                 // the accumulator is free once every lane has read it
+                    tc_fence_before();
+                    __syncthreads();
+                    if (tid == 0) {
+                        tc_fence_after();
+                        tc_issue_chunk(tbase, stage, ones, np, c + 1, mb_mma);
+                    }
+                }
+            }
+
+            // Parameter.step decision tree, :334-367
+            const double llp = acc * m_prop - r_prop;
+            const double post_prop = lp_prop + llp;
+            const double post_cur = lp_cur + ll_cur;
+            const double diff = post_prop - post_cur;
+            const bool b1 = !finite64(post_cur) && finite64(post_prop);
+            const bool test = finite64(llp) && finite64(diff);         // branches 4/5 draw the uniform
+            const int fast = log_u_vs_diff_fast(u, diff);
+            bool accept = b1 || (test && fast > 0);
+            if (!b1 && test && fast == 0) accept = log(u) < diff;      // rare: within 1e-6 of the threshold
+            if (GENERAL) {
+                if (trace && on) {
+                    a.tr_ll[at] = llp;
+                    a.tr_lp[at] = lp_prop;
+                    a.tr_diff[at] = diff;
+                    a.tr_acc[at] = accept ? 1 : 0;
+                }
+                if (forced) accept = a.tape_acc[at] != 0;
+            }
+            if (accept) {                                              // :369-378, :608-610
+                if (on) {
+                    a.theta[at] = prop;
+                    if (!partial) a.lprior[at] = lp_prop;
+                }
+                ll_cur = llp;
+                aux_m = m_prop;
+                aux_r = r_prop;
+            }
+            if (!is_sigma) {                                           // column p <- the value the chain keeps
+                const float wkeep = accept ? wprop : wcur;
+                const unsigned h = tf32_rn(wkeep);
+                tmem_st1(tlane + MCMCN_TC_A_HI + p, h);
+                tmem_st1(tlane + MCMCN_TC_A_LO + p, tf32_rn(wkeep - __uint_as_float(h)));
+            }
+            if (count && on) {
+                unsigned cnt = a.counts[at];
+                cnt += accept ? 1u : 0x10000u;
+                if (a.tune) {                                          // Parameter.tune, :385-437
+                    const unsigned na = cnt & 0xFFFFu, nrj = cnt >> 16;
+                    if (na + nrj) {
+                        const double sc = a.scale[at];
+                        const double rate = (double)na / (double)(na + nrj);
+                        double f = 1.0;
+                        if (rate < 0.001) f = 0.1;
+                        else if (rate < 0.05) f = 0.5;
+                        else if (rate < 0.2) f = 0.9;
+                        else if (rate > 0.95) f = 10.0;
+                        else if (rate > 0.75) f = 2.0;
+                        else if (rate > 0.5) f = 1.1;
+                        double ns = __dmul_rn(sc, f);
+                        if (ns == 0.0) ns = sc;
+                        a.scale[at] = ns;
+                        cnt = 0;
+                    }
+                }
+                a.counts[at] = cnt;
+            }
+        }
+        if (on) a.ll[(size_t)g * S + chl] = ll_cur;
+        // every MMA that read this stage has completed (all threads waited on its mbarrier)
+        if (tid == 0 && g + 2 < g1) stage_group(s, g + 2);
+    }
+    tmem_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_free(tbase, MCMCN_TC_COLS);
+}
+
+}  // namespace mcmcn

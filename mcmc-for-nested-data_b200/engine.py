@@ -156,6 +156,9 @@ class Engine(object):
         self._group_nobs = torch.from_numpy(group_nobs).to(dev)
         self._task_group0 = torch.from_numpy(self._task_group0_h).to(dev)
         self._obj_const = torch.from_numpy(obj_const).to(dev) if obj_const is not None else None
+        tcData, tcOff = getattr(objective, "tcData", None), getattr(objective, "tcGroupOff", None)
+        self._tc_data = torch.from_numpy(tcData).to(dev) if tcData is not None else None
+        self._tc_group_off = torch.from_numpy(tcOff).to(dev) if tcData is not None else None
 
         m = nat.Model()
         m.objective = objective.kind
@@ -175,6 +178,8 @@ class Engine(object):
         m.group_off_host = self._group_off_h.ctypes.data_as(ctypes.c_void_p)
         m.obj_const = _ptr(self._obj_const)
         m.user_objective = objective.userHandle
+        m.tc_data, m.tc_group_off = _ptr(self._tc_data), _ptr(self._tc_group_off)
+        m.tc_max_block_floats = int(numpy.diff(tcOff).max()) if tcData is not None else 0
         if not self.partial:
             for p, d in enumerate(priorDistribution):
                 m.prior[p] = priorFromScipy(d)

@@ -51,6 +51,7 @@ class Model(ctypes.Structure):
                 ("task_group0", c_void_p), ("task_group0_host", c_void_p),
                 ("group_off_host", c_void_p), ("obj_const", c_void_p),
                 ("user_objective", c_void_p),
+                ("tc_data", c_void_p), ("tc_group_off", c_void_p), ("tc_max_block_floats", ctypes.c_int64),
                 ("prior", Prior * MAX_PARAMS)]
 
 
