@@ -172,6 +172,40 @@ def workloadConfig(args, chains):
                   % (chains * args.groups * (args.coef + 1) * 28 / 1e6)}
 
 
+def roofline(args, tensorCore, sweepMs, chains, peakFp32, peakTf32, peakMufu):
+    """Roofline of the step kernel.  Algorithmic work per chain-observation
+    log-density evaluation: 2K+4 = 20 FP32 flop.
+    FP32-pipe kernel: bound by the FP32 pipe, achieved = 20 flop/eval over the launch time.
+    tcgen05 kernel: the contraction runs on the tensor pipe as 3xTF32 -- per 128-chain x group tile
+    and sweep, 4 MMAs (A_hi.X_hi, A_lo.X_hi, A_hi.X_lo, 1.NE) of 2*128*Np*8 flop, Np = the group's
+    observations rounded up to 16 -- and that pipe is the one that binds once latencies are hidden,
+    so achieved = those TF32 flop over the launch time against the pipe's measured MMA rate."""
+    G, R, K = args.groups, args.obs, args.coef
+    P, N = K + 1, G * R
+    algFlops = FLOP_PER_EVAL * P * N * chains
+    algTflops = algFlops / (sweepMs * 1e-3) / 1e12
+    common = {"flop_per_eval": FLOP_PER_EVAL, "algorithmic_fp32_tflops": algTflops,
+              "fp32_pipe_peak_tflops": peakFp32 / 1e12, "mufu_peak_gops": peakMufu / 1e9,
+              "traffic": args.traffic if tensorCore else args.traffic_pipe}
+    if not tensorCore:
+        common.update({"bound": "fp32", "kernel": "sweep_kernel<LinReg<8>,4,float>", "achieved": algTflops,
+                       "peak": peakFp32 / 1e12, "unit": "TFLOP/s", "frac": algFlops / (sweepMs * 1e-3) / peakFp32,
+                       "peak_source": "FP32 pipe limit measured in this run by an FFMA-only microbenchmark "
+                                      "(mcmcn_peak_fp32); MEASURED_PEAKS.json has no FP32 figure; nominal 74.4"})
+        return common
+    npad = max(16, (R + 15) // 16 * 16)
+    tiles = ((chains + 127) // 128) * G * P
+    tf32Flops = tiles * 4 * 2.0 * 128 * npad * 8
+    common.update({"bound": "tensor", "kernel": "sweep_tc_kernel (tcgen05.mma kind::tf32, 3xTF32 + ne)",
+                   "achieved": tf32Flops / (sweepMs * 1e-3) / 1e12, "peak": peakTf32 / 1e12, "unit": "TFLOP/s",
+                   "frac": tf32Flops / (sweepMs * 1e-3) / peakTf32,
+                   "tf32_flop_per_eval": tf32Flops / (P * N * chains),
+                   "peak_source": "tensor pipe limit for this MMA shape (M128 N208 K8 kind::tf32, A in TMEM) measured "
+                                  "in this run by an MMA-only microbenchmark (mcmcn_peak_tf32); MEASURED_PEAKS.json "
+                                  "has bf16 only (1658 TFLOP/s burst; TF32 runs at half the bf16 rate = 829)"})
+    return common
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def runGpu(args):
     import torch
@@ -209,6 +243,10 @@ def runGpu(args):
     peakFlops = peak.value
     mufu = ctypes.c_double(0.0)
     nat.check(lib.mcmcn_peak_mufu(ctypes.byref(mufu), eng.stream))
+    tensorCore = eng.usesTensorCore
+    peakTf32 = ctypes.c_double(0.0)
+    if tensorCore:
+        nat.check(lib.mcmcn_peak_tf32(ctypes.byref(peakTf32), eng.stream))
 
     def barrier():
         if world > 1:
@@ -233,7 +271,8 @@ def runGpu(args):
 
     # ---- pass 2: same steps through host buffers (H2D of the observation data, D2H of the
     # rows the step retained and of the hyper-parameters), fresh Philox seed
-    pinData = torch.from_numpy(eng._data.cpu().numpy()).pin_memory()
+    stepInput = eng.stepInput           # the observation blocks the step kernel reads
+    pinData = torch.from_numpy(stepInput.cpu().numpy()).pin_memory()
     rowBytes = eng.nCol * eng.S * 4
     maxRows = ips // thin + 1
     pinRows = torch.empty((maxRows, eng.nCol, eng.S), dtype=torch.float32).pin_memory()
@@ -246,7 +285,7 @@ def runGpu(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(args.steps):
-        eng._data.copy_(pinData, non_blocking=True)
+        stepInput.copy_(pinData, non_blocking=True)
         r0 = len(store.iterations)
         eng.run((args.warmup + k) * ips, ips, burn, thin, store=store)
         r1 = len(store.iterations)
@@ -268,8 +307,6 @@ def runGpu(args):
         value = chainIters / (ms * 1e-3)
         e2e = chainIters / (msE2e * 1e-3)
         sweepMs = timing[0] / max(timing[6], 1.0)
-        flopsPerLaunch = FLOP_PER_EVAL * P * N * chains
-        achieved = flopsPerLaunch / (sweepMs * 1e-3)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -284,14 +321,7 @@ def runGpu(args):
                               "writeback_avg": timing[2] / max(timing[8], 1.0),
                               "timed_launches": int(timing[6] + timing[7] + timing[8]),
                               "step_kernel_share": sweepMs * timing[3] / ms},
-                "roofline": {"bound": "fp32", "kernel": "sweep_kernel<LinReg<8>,4,float>",
-                             "achieved": achieved / 1e12, "peak": peakFlops / 1e12, "unit": "TFLOP/s",
-                             "frac": achieved / peakFlops,
-                             "peak_source": "FP32 pipe limit measured in this run by an FFMA-only microbenchmark "
-                                            "(mcmcn_peak_fp32, one live register per FFMA); MEASURED_PEAKS.json has no "
-                                            "FP32 figure; nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
-                             "flop_per_eval": FLOP_PER_EVAL, "traffic": args.traffic,
-                             "mufu_peak_gops": mufu.value / 1e9},
+                "roofline": roofline(args, tensorCore, sweepMs, chains, peakFlops, peakTf32.value, mufu.value),
                 "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline:
             v, dt = cpuBaseline(args, 1, args.cpu_iters)
@@ -320,9 +350,11 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=40)
     ap.add_argument("--ref-iters", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--traffic", type=float, default=204.2e6,
+    ap.add_argument("--traffic", type=float, default=208.0e6,
                     help="dram__bytes_read.sum + dram__bytes_write.sum per step-kernel launch, from the committed "
-                         "ncu --set full capture (profiles/r1_sweep_kernel_ncu_summary.txt); not measured live")
+                         "ncu --set full capture (profiles/r1_tc_kernel_ncu_summary.txt); not measured live")
+    ap.add_argument("--traffic-pipe", type=float, default=204.2e6,
+                    help="same for the FP32-pipe kernel (profiles/r1_sweep_kernel_ncu_summary.txt)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         print("warning: the timing rules ask for >= 3 warm-up steps", file=sys.stderr)

@@ -176,6 +176,11 @@ int mcmcn_tile_capacity_bytes(void);
 /* Is (objective, n_coef, n_params, precision) compiled in? 1 yes, 0 no. */
 int mcmcn_supported(int objective, int n_params, int n_coef, int precision);
 
+/* Will mcmcn_run advance this model with the tcgen05 step kernel (1) or the FP32-pipe kernel (0)?
+ * (linear_regression, precision 32, K <= 8, tc_data given, every group block within the stage
+ * capacity; environment variable MCMCN_NO_TC=1 forces 0.) */
+int mcmcn_uses_tensor_core(const mcmcn_model* model);
+
 /* Replaces Sampler._loop + StepMethod.step (posteriorSampling.py:594-613, :862-896). */
 int mcmcn_run(const mcmcn_model* model, const mcmcn_state* state,
               const mcmcn_run_args* args, void* stream);
@@ -227,10 +232,12 @@ int mcmcn_diag_median_hdi(const double* sorted, int64_t n_keys, int64_t len, int
                           double* out, void* stream);
 
 /* ---- measured pipe peaks for the roofline -----------
- * Run an FFMA-only / MUFU-only microbenchmark on the current device and return
- * the achieved rate in *out (FP32 flop/s, MUFU op/s). */
+ * Run an FFMA-only / MUFU-only / MMA-only microbenchmark on the current device and return
+ * the achieved rate in *out (FP32 flop/s, MUFU op/s, TF32 flop/s). */
 int mcmcn_peak_fp32(double* out_flops, void* stream);
 int mcmcn_peak_mufu(double* out_ops, void* stream);
+/* tensor pipe: back-to-back tcgen05.mma kind::tf32 of the step kernel's shape (M 128, N 208, K 8), FLOP/s */
+int mcmcn_peak_tf32(double* out_flops, void* stream);
 
 /* ---- user objectives (north star (1): documented C ABI, compiled by NVRTC) ----
  * `source` is CUDA C++ that defines, at namespace scope,

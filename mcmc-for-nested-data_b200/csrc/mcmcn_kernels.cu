@@ -45,7 +45,7 @@ static cudaError_t launch_sweep(sweep_fn fn, dim3 grid, dim3 block, size_t smem,
 
 static const KernelSet* find_set(int objective, int P, int K, int precision) {
     typedef const KernelSet* (*getter)(int*);
-    static const getter getters[] = {sets_linreg_a, sets_linreg_b, sets_linreg_c, sets_logit, sets_gauss};
+    static const getter getters[] = {sets_linreg_a, sets_linreg_b, sets_linreg_c, sets_linreg_d, sets_linreg_e, sets_logit, sets_gauss};
     for (getter get : getters) {
         int n = 0;
         const KernelSet* sets = get(&n);
@@ -189,6 +189,8 @@ extern "C" {
 int mcmcn_version(void) { return MCMCN_VERSION; }
 const char* mcmcn_last_error(void) { return g_last_error.c_str(); }
 int mcmcn_tile_capacity_bytes(void) { return kTileCapBytes; }
+
+int mcmcn_uses_tensor_core(const mcmcn_model* m) { return (m && tc_eligible(m)) ? 1 : 0; }
 
 int mcmcn_supported(int objective, int n_params, int n_coef, int precision) {
     return find_set(objective, n_params, n_coef, precision) ? 1 : 0;

@@ -4,8 +4,45 @@
 #include <cuda_runtime.h>
 
 #include "mcmcn_host.h"
+#include "mcmcn_tc.cuh"
 
 namespace mcmcn {
+
+// The tensor pipe's own limit for the MMA the step kernel issues: back-to-back
+// tcgen05.mma kind::tf32, M = 128, N = 208, K = 8, A in tensor memory, B in shared memory,
+// two CTAs per SM.  Operand contents are irrelevant to the rate (zeros).
+__global__ void __launch_bounds__(128) tf32_peak_kernel(int reps) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ unsigned base_s;
+    __shared__ unsigned long long mbar_s;
+    const unsigned mb = smem_u32(&mbar_s);
+    for (int i = threadIdx.x; i < 208 * 8; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 0.0f;
+    if (threadIdx.x == 0) mbar_init(mb, 1);
+    if (threadIdx.x < 32) tmem_alloc(&base_s, 256);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tbase = base_s;
+    {
+        unsigned z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        tmem_st8(tbase + ((threadIdx.x >> 5) << 21) + 224, z);
+        tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tc_fence_after();
+        const unsigned long long bdesc = tc_smem_desc(smem_u32(smem), 128, 256);
+        const unsigned idesc = tc_idesc(128, 208);
+        for (int r = 0; r < reps; ++r) mma_tf32_ts(tbase, tbase + 224, bdesc, idesc, r > 0);
+        mma_commit(mb);
+    }
+    mbar_wait(mb, 0);
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_free(tbase, 256);
+}
 
 // 16 independent accumulators per thread, one live register per FFMA (a = a*x + y): the operand
 // pattern that reaches the FP32 pipe's own limit (124.6 of 128 lanes/clk/SM on B200).  Patterns
@@ -90,6 +127,17 @@ int mcmcn_peak_fp32(double* out_flops, void* stream_) {
     const int rc = time_kernel([&] { ffma_peak_kernel<<<blocks, threads, 0, stream>>>(d, iters, 1.0f); }, flops, out_flops, stream);
     cudaFree(d);
     return rc;
+}
+
+int mcmcn_peak_tf32(double* out_flops, void* stream_) {
+    if (!out_flops) { set_error("null output"); return MCMCN_ERR_INVALID; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int dev = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int reps = 8000, blocks = sms * 2;
+    const double flops = 2.0 * 128 * 208 * 8 * (double)reps * blocks;
+    return time_kernel([&] { tf32_peak_kernel<<<blocks, 128, 208 * 32, stream>>>(reps); }, flops, out_flops, stream);
 }
 
 int mcmcn_peak_mufu(double* out_ops, void* stream_) {

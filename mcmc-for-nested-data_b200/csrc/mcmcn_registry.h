@@ -32,6 +32,8 @@ struct KernelSet {
 const KernelSet* sets_linreg_a(int* n);
 const KernelSet* sets_linreg_b(int* n);
 const KernelSet* sets_linreg_c(int* n);
+const KernelSet* sets_linreg_d(int* n);
+const KernelSet* sets_linreg_e(int* n);
 const KernelSet* sets_logit(int* n);
 const KernelSet* sets_gauss(int* n);
 sweep_fn tc_sweep_kernel(int f);    // mcmcn_sets_tc.cu

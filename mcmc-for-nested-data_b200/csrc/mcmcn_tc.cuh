@@ -163,12 +163,19 @@ __device__ __forceinline__ double tc_sum_squares(unsigned addr, int pieces) {
 // decisions of earlier sweeps of the same iteration, so it is fetched one sweep ahead.
 struct TcInputs {
     double cur, sc, z, u;
+    double bbar;                    // reference point of this coefficient (0 for sigma)
     double h_mu, h_lsd, h_isd;      // partial pooling: this name's hyper-parameters
     double lp_cur;                  // fixed priors / log-prior override: stored log-prior of the current value
 };
 
+// One Philox4x32-10 call serves two consecutive sweeps: Box-Muller turns words 0-1 into two
+// standard normals (cosine and sine branch), words 2 and 3 give one 32-bit uniform each,
+// (w + 0.5) * 2^-32 in (0, 1).  `stash` carries the second pair to the odd sweep.
+struct TcStash { double z, u; };
+
 template <bool GENERAL>
-__device__ __forceinline__ TcInputs tc_fetch(const SweepArgs& a, int p, int g, int chl, bool partial, bool replay, bool override_lp) {
+__device__ __forceinline__ TcInputs tc_fetch(const SweepArgs& a, int p, int g, int chl, bool partial, bool replay, bool override_lp,
+                                             TcStash& stash) {
     const int P = a.P;
     const size_t S = (size_t)a.S;
     const size_t row = ((size_t)p * a.G + g) * S;
@@ -176,6 +183,7 @@ __device__ __forceinline__ TcInputs tc_fetch(const SweepArgs& a, int p, int g, i
     o.cur = a.theta[row + chl];
     o.sc = a.scale[row + chl];
     o.h_mu = o.h_lsd = o.h_isd = o.lp_cur = 0.0;
+    o.bbar = p < P - 1 ? a.obj_const[(size_t)g * (P - 1) + p] : 0.0;
     if (partial) {
         o.h_mu = a.hyper[((size_t)0 * P + p) * S + chl];
         o.h_lsd = a.hyper[((size_t)3 * P + p) * S + chl];
@@ -188,11 +196,33 @@ __device__ __forceinline__ TcInputs tc_fetch(const SweepArgs& a, int p, int g, i
         o.z = a.tape_z[row + chl];
         o.u = a.tape_u[row + chl];
     } else {
-        const uint4 rnd = philox_draw(a.chain_id0 + chl, a.seed, a.iter, MCMCN_STREAM_SWEEP, (unsigned)(p * a.G + g), 0u);
-        o.z = normal_from(rnd.x, rnd.y);
-        o.u = uniform_from(rnd.z, rnd.w);
+        if ((p & 1) == 0) {
+            const uint4 rnd = philox_draw(a.chain_id0 + chl, a.seed, a.iter, MCMCN_STREAM_SWEEP, (unsigned)((p >> 1) * a.G + g), 1u);
+            const float u1 = (float)((rnd.x >> 8) + 1u) * 5.9604644775390625e-8f;   // (0, 1]
+            const float u2 = (float)(rnd.y >> 8) * 5.9604644775390625e-8f;          // [0, 1)
+            float r;
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));
+            o.z = (double)(r * __cosf(6.283185307179586f * u2));
+            stash.z = (double)(r * __sinf(6.283185307179586f * u2));
+            o.u = ((double)rnd.z + 0.5) * 2.3283064365386963e-10;
+            stash.u = ((double)rnd.w + 0.5) * 2.3283064365386963e-10;
+        } else {
+            o.z = stash.z;
+            o.u = stash.u;
+        }
     }
     return o;
+}
+
+// CTA-wide rendezvous before an MMA issue: every lane's tensor-memory traffic (tcgen05.st of the
+// A operand, tcgen05.ld of the accumulator) is ordered before the barrier, thread 0 issues after
+// it.  (A rendezvous on a shared-memory atomic where the last warp to arrive issues and nobody
+// waits measured 7 % slower: atom.acq_rel costs a MEMBAR per warp.)
+__device__ __forceinline__ bool tc_rendezvous_issuer() {
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) tc_fence_after();
+    return threadIdx.x == 0;
 }
 
 // grid = (group ranges, chain blocks of 128); block = 128 threads; dynamic shared memory =
@@ -257,6 +287,8 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
     const int chl = min(ch, a.n_chains - 1);                           // lanes past the last chain redo its work, store nothing
     const size_t S = (size_t)a.S;
     unsigned tma_phase = 0, mma_phase = 0;
+    TcStash stash;
+    stash.z = stash.u = 0.0;
 
     for (int g = g0; g < g1; ++g) {
         const int s = (g - g0) & 1;
@@ -266,7 +298,12 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
         const unsigned stage = stage0 + (unsigned)s * (unsigned)a.tc_stage_bytes;
         const double* bbar = a.obj_const + (size_t)g * K;
 
-        TcInputs in = tc_fetch<GENERAL>(a, 0, g, chl, partial, replay, override_lp);
+        TcInputs in = tc_fetch<GENERAL>(a, 0, g, chl, partial, replay, override_lp, stash);
+        if (g + 1 < g1) {                                              // next group's state: DRAM -> L2 meanwhile
+            for (int k = 0; k < P; ++k)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.theta + ((size_t)k * a.G + g + 1) * S + chl));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ll + (size_t)(g + 1) * S + chl));
+        }
         {   // A operand of the current state: centred coefficients (FP32), split hi / lo
             unsigned hi[8], lo[8];
 #pragma unroll
@@ -297,7 +334,8 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
         for (int p = 0; p < P; ++p) {
             const size_t at = ((size_t)p * a.G + g) * S + chl;
             const bool is_sigma = p == K;
-            // proposal and log-priors (pure functions of state known before the sweep)
+            // proposal and log-priors (pure functions of state known before the sweep; the reference
+            // evaluates them after the likelihood, :335, :331)
             const double prop = __dadd_rn(in.cur, __dmul_rn(in.sc, in.z));     // numpy.random.normal(value, sd), :304-306
             double lp_prop, lp_cur;
             if (partial) {
@@ -320,21 +358,16 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
                     r_prop = (double)R * (log(sg) + MCMCN_LOG_SQRT_2PI);
                 }
             } else {                                                   // column p of the A operand <- the proposal
-                wcur = (float)__dsub_rn(in.cur, bbar[p]);
-                wprop = (float)__dsub_rn(prop, bbar[p]);
+                wcur = (float)__dsub_rn(in.cur, in.bbar);
+                wprop = (float)__dsub_rn(prop, in.bbar);
                 const unsigned h = tf32_rn(wprop);
                 tmem_st1(tlane + MCMCN_TC_A_HI + p, h);
                 tmem_st1(tlane + MCMCN_TC_A_LO + p, tf32_rn(wprop - __uint_as_float(h)));
             }
             tmem_wait_st();
-            tc_fence_before();
-            __syncthreads();
-            if (tid == 0) {
-                tc_fence_after();
-                tc_issue_chunk(tbase, stage, ones, np, 0, mb_mma);
-            }
+            if (tc_rendezvous_issuer()) tc_issue_chunk(tbase, stage, ones, np, 0, mb_mma);
             // while the tensor core works: state and random numbers of the next sweep
-            if (p + 1 < P) in = tc_fetch<GENERAL>(a, p + 1, g, chl, partial, replay, override_lp);
+            if (p + 1 < P) in = tc_fetch<GENERAL>(a, p + 1, g, chl, partial, replay, override_lp, stash);
 
             double acc = 0.0;
             for (int c = 0; c < nchunks; ++c) {
@@ -344,12 +377,7 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
                 const int nc = min(MCMCN_TC_CH, np - c * MCMCN_TC_CH);
                 acc += tc_sum_squares(tlane + MCMCN_TC_D, nc >> 4);
                 if (c + 1 < nchunks) {                                 // the accumulator is free once every lane has read it
-                    tc_fence_before();
-                    __syncthreads();
-                    if (tid == 0) {
-                        tc_fence_after();
-                        tc_issue_chunk(tbase, stage, ones, np, c + 1, mb_mma);
-                    }
+                    if (tc_rendezvous_issuer()) tc_issue_chunk(tbase, stage, ones, np, c + 1, mb_mma);
                 }
             }
 

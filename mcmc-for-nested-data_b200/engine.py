@@ -209,6 +209,16 @@ class Engine(object):
 
     # ------------------------------------------------------------------ helpers
     @property
+    def usesTensorCore(self):
+        """True when mcmcn_run advances this model with the tcgen05 step kernel."""
+        return bool(self.lib.mcmcn_uses_tensor_core(ctypes.byref(self.model)))
+
+    @property
+    def stepInput(self):
+        """The device tensor of observation data the step kernel reads."""
+        return self._tc_data if self.usesTensorCore else self._data
+
+    @property
     def stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 

@@ -10,7 +10,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmcmcn.so")
+LIB_PATH = os.environ.get("MCMCN_LIB", os.path.join(HERE, "libmcmcn.so"))   # MCMCN_LIB: A/B builds of the same ABI
 
 MAX_PARAMS = 17
 
@@ -82,6 +82,7 @@ PROTOTYPES = {
     "mcmcn_last_error": (ctypes.c_char_p, []),
     "mcmcn_tile_capacity_bytes": (ctypes.c_int, []),
     "mcmcn_supported": (ctypes.c_int, [ctypes.c_int] * 4),
+    "mcmcn_uses_tensor_core": (ctypes.c_int, [ctypes.POINTER(Model)]),
     "mcmcn_run": (ctypes.c_int, [ctypes.POINTER(Model), ctypes.POINTER(State),
                                  ctypes.POINTER(RunArgs), c_void_p]),
     "mcmcn_timing_collect": (ctypes.c_int, []),
@@ -104,6 +105,7 @@ PROTOTYPES = {
                                              c_void_p, c_void_p]),
     "mcmcn_peak_fp32": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), c_void_p]),
     "mcmcn_peak_mufu": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), c_void_p]),
+    "mcmcn_peak_tf32": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), c_void_p]),
     "mcmcn_user_objective_compile": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32,
                                                     ctypes.c_int32, ctypes.c_int32,
                                                     ctypes.POINTER(c_void_p)]),

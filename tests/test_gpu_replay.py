@@ -71,15 +71,67 @@ def test_replay_mle_start_regression_example():
     numpy.testing.assert_allclose(res.rows, res.oracleRows, rtol=1e-9, atol=1e-9)
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("fp64", 1e-11)])
-def test_replay_c3_shape_wide_path(precision, tol):
-    """C3's shape (K = 8 coefficients + sigma, R = 200) on the 4-chains-per-lane kernel,
-    with a chain count that leaves partial warps."""
+@pytest.mark.parametrize("precision,tol,tensorCore", [("fp32", 1e-5, True), ("fp32", 1e-5, False), ("fp64", 1e-11, False)])
+def test_replay_c3_shape_wide_path(precision, tol, tensorCore, monkeypatch):
+    """C3's shape (K = 8 coefficients + sigma, R = 200) on the tcgen05 step kernel (two
+    accumulator chunks of 112 + 96 observations) and on the 4-chains-per-lane FP32-pipe kernel,
+    with a chain count that leaves partial warps / lanes."""
+    if not tensorCore:
+        monkeypatch.setenv("MCMCN_NO_TC", "1")
     obj, names, nResp, ranges = parity.syntheticRegression(G=6, R=200, K=8)
     res = parity.replay(obj, names, 6, nResp, "partial", None, ranges, nChains=133, nIter=25,
                         nSamples=10, precision=precision)
     err, ties = parity.checkReplay(res, tol, 1e-4)
     numpy.testing.assert_allclose(res.rows, res.oracleRows, rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("G,R,K,ragged,pooling,nChains", [
+    (5, 250, 8, False, "partial", 130),      # three accumulator chunks (112 + 112 + 32), two chain blocks
+    (9, 40, 3, True, "partial", 5),          # ragged groups of 1..79 observations, K < 8
+    (4, 112, 8, False, "none", 1),           # exactly one full chunk, fixed priors, a single chain
+    (7, 200, 5, False, "partial", 257),      # three chain blocks, the last with one chain
+])
+def test_replay_tensor_core_kernel_shapes(G, R, K, ragged, pooling, nChains):
+    """The tcgen05 step kernel over the shapes that change its control flow: number of
+    accumulator chunks, padding rows, unused coefficient slots, lanes past the last chain."""
+    obj, names, nResp, ranges = parity.syntheticRegression(G=G, R=R, K=K, ragged=ragged)
+    prior = None
+    if pooling == "none":
+        prior = [scipy.stats.norm(0, 10)] * K + [scipy.stats.gamma(2)]
+    res = parity.replay(obj, names, G, nResp, pooling, prior, ranges, nChains=nChains, nIter=20,
+                        nSamples=10, precision="fp32")
+    err, ties = parity.checkReplay(res, 1e-5, 1e-4)
+    numpy.testing.assert_allclose(res.rows, res.oracleRows, rtol=1e-9, atol=1e-9)
+
+
+def test_tensor_core_and_fp32_pipe_kernels_agree_at_c3_size(monkeypatch):
+    """BASELINE config 3 at full width (1,024 groups x 200 observations x 8 coefficients,
+    1,024 chains): one traced iteration on the tcgen05 kernel and on the FP32-pipe kernel from
+    the same state and the same replay tape; every proposal log-likelihood must agree
+    within 2e-5 relative (each is within 1e-5 of the FP64 oracle on the shapes the oracle can do)."""
+    import torch
+    from engine import Engine
+    obj, names, nResp, ranges = parity.syntheticRegression(G=1024, R=200, K=8)
+    nC, G, P = 1024, 1024, 9
+    out = {}
+    for label, env in (("tc", None), ("pipe", "1")):
+        if env:
+            monkeypatch.setenv("MCMCN_NO_TC", env)
+        eng = Engine(parity.deviceObjective(obj, nResp, "fp32"), G, nResp, "partial", nC, seed=7)
+        eng.initialise(names, ranges)
+        gen = torch.Generator(device="cpu").manual_seed(11)
+        tape = {"z": torch.randn((1, P, G, eng.S), generator=gen, dtype=torch.float64).mul_(0.05).to(eng.device),
+                "u": torch.rand((1, P, G, eng.S), generator=gen, dtype=torch.float64).to(eng.device),
+                "accept": (torch.rand((1, P, G, eng.S), generator=gen) < 0.4).to(torch.uint8).to(eng.device),
+                "zmu": torch.randn((1, P, eng.S), generator=gen, dtype=torch.float64).to(eng.device),
+                "qsig": torch.rand((1, P, eng.S), generator=gen, dtype=torch.float64).add_(0.5).to(eng.device)}
+        tr = eng.run(0, 1, 0, 1, tape=tape, trace=True)
+        torch.cuda.synchronize()
+        out[label] = (tr["ll"][..., :nC].cpu().numpy(), eng.getState()["theta"])
+    # a proposed sigma <= 0 gives NaN on both kernels (scipy's scale check, :354-356); relErr wants the same NaN
+    assert numpy.isfinite(out["tc"][0]).mean() > 0.99
+    assert parity.relErr(out["tc"][0], out["pipe"][0]).max() <= 2e-5
+    numpy.testing.assert_array_equal(out["tc"][1], out["pipe"][1])      # forced decisions: identical states
 
 
 @pytest.mark.parametrize("pooling", ["partial", "none"])

@@ -305,5 +305,14 @@ int main() {
                "%.1f TFLOP/s tf32 chip-wide\n", per_sm, (double)mx / (reps * 4), NOBS,
                ms * 1e-3 * khz * 1e3 / (reps * 4.0 * per_sm), 2.0 * 128 * NOBS * 8 * reps * 4.0 * grid / (ms * 1e-3) / 1e12);
     }
+    // MMA round-trip latency: first issue -> mbarrier completion observed, one CTA, 4 MMAs (one chunk)
+    for (int reps = 1; reps <= 4; reps *= 2) {
+        mma_kernel<<<1, 128, 3 * SLAB>>>(d_slabs, d_coef, d_out, 0, reps, clk);
+        CK(cudaDeviceSynchronize());
+        mma_kernel<<<1, 128, 3 * SLAB>>>(d_slabs, d_coef, d_out, 0, reps, clk);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(h.data(), clk, sizeof(long long), cudaMemcpyDeviceToHost));
+        printf("mma latency: %d x 4 MMAs (N=%d) issue -> mbarrier observed: %lld clk\n", reps, NOBS, h[0]);
+    }
     return 0;
 }
