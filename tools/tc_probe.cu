@@ -211,6 +211,55 @@ __global__ void __launch_bounds__(128) mma_kernel(const float* slabs, const floa
     if (threadIdx.x < 32) tmem_free(tbase, 256);
 }
 
+// The step kernel's MMA stream: per "sweep" two chunks (N = n0, then n1) of 4 MMAs each, a commit per
+// chunk, optionally waiting for each commit before issuing the next chunk (as the kernel must, its
+// accumulator being single-buffered).  128 TMEM columns per CTA so that four CTAs share an SM.
+__global__ void __launch_bounds__(128) mma_stream_kernel(int n0, int n1, int sweeps, int wait_each, long long* clk) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ unsigned base_s;
+    __shared__ unsigned long long mbar_s;
+    const unsigned mb = smem_u32(&mbar_s);
+    float* sm = reinterpret_cast<float*>(smem);
+    for (int i = threadIdx.x; i < 3 * SLAB / 4; i += blockDim.x) sm[i] = 0.f;
+    if (threadIdx.x == 0) mbar_init(mb, 1);
+    if (threadIdx.x < 32) tmem_alloc(&base_s, 128);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const unsigned tbase = base_s;
+    unsigned z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    sttm8(tbase + ((threadIdx.x >> 5) << 21) + 112, z);
+    sttm8(tbase + ((threadIdx.x >> 5) << 21) + 120, z);
+    wait_st();
+    fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        fence_after();
+        const unsigned s0 = smem_u32(smem);
+        unsigned parity = 0;
+        const long long t0 = clock64();
+        for (int sw = 0; sw < sweeps; ++sw) {
+            for (int c = 0; c < 2; ++c) {
+                const int n = c ? n1 : n0;
+                if (n == 0) continue;
+                const unsigned id = idesc_tf32(128, n);
+                const unsigned base = s0 + (c ? n0 * 32 : 0);
+                mma_tf32_ts(tbase, tbase + 112, smem_desc(base, 128, 256), id, 0);
+                mma_tf32_ts(tbase, tbase + 120, smem_desc(base, 128, 256), id, 1);
+                mma_tf32_ts(tbase, tbase + 112, smem_desc(base + SLAB, 128, 256), id, 1);
+                mma_tf32_ts(tbase, tbase + 120, smem_desc(base + 2 * SLAB, 128, 256), id, 1);
+                if (wait_each) { mma_commit(mb); mbar_wait(mb, parity); parity ^= 1; }
+            }
+        }
+        if (!wait_each) { mma_commit(mb); mbar_wait(mb, 0); }   // one commit covers everything issued before it
+        clk[blockIdx.x] = clock64() - t0;
+    }
+    fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_free(tbase, 128);
+}
+
 static float tf32_trunc(float v) { uint32_t u; memcpy(&u, &v, 4); u &= 0xFFFFE000u; float r; memcpy(&r, &u, 4); return r; }
 
 int main() {
@@ -304,6 +353,26 @@ int main() {
         printf("mma rate, %d CTA/SM: %.1f clk per M128 N%d K8 tf32 MMA per CTA (in-kernel), %.1f clk per MMA per SM by wall; "
                "%.1f TFLOP/s tf32 chip-wide\n", per_sm, (double)mx / (reps * 4), NOBS,
                ms * 1e-3 * khz * 1e3 / (reps * 4.0 * per_sm), 2.0 * 128 * NOBS * 8 * reps * 4.0 * grid / (ms * 1e-3) / 1e12);
+    }
+    // the step kernel's MMA stream, 1 and 4 CTAs per SM
+    CK(cudaFuncSetAttribute(mma_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * SLAB));
+    {
+        const int shapes[4][2] = {{208, 0}, {112, 96}, {112, 0}, {96, 0}};
+        for (int per_sm = 1; per_sm <= 4; per_sm *= 4)
+            for (int wait_each = 0; wait_each <= 1; ++wait_each)
+                for (auto& sh : shapes) {
+                    if (per_sm > 2 && sh[0] > 112) continue;   // 128 TMEM columns per CTA
+                    const int sweeps = 1000, grid = sms * per_sm;
+                    for (int rep = 0; rep < 2; ++rep) {
+                        CK(cudaEventRecord(e0));
+                        mma_stream_kernel<<<grid, 128, 3 * SLAB>>>(sh[0], sh[1], sweeps, wait_each, clk);
+                        CK(cudaEventRecord(e1));
+                        CK(cudaDeviceSynchronize());
+                    }
+                    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+                    printf("mma stream N=%d+%d, %d CTA/SM, %s: %.0f clk per sweep (8 or 4 MMAs) per SM by wall\n", sh[0], sh[1], per_sm,
+                           wait_each ? "wait after each chunk" : "back to back", ms * 1e-3 * khz * 1e3 / (sweeps * (double)per_sm));
+                }
     }
     // MMA round-trip latency: first issue -> mbarrier completion observed, one CTA, 4 MMAs (one chunk)
     for (int reps = 1; reps <= 4; reps *= 2) {
