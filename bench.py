@@ -50,6 +50,20 @@ def makeWorkload(G, R, K, seed=20261018):
     return X, y, names, ranges
 
 
+def makeLogitWorkload(G, R, seed=20261019):
+    """SURVEY.md section 8d config C5: x ~ N(0,1); a_g ~ N(0,1), b_g ~ N(1,0.5);
+    y ~ Bernoulli(sigmoid(a_g + b_g x)); parameters (a, b)."""
+    rs = numpy.random.RandomState(seed)
+    N = G * R
+    x = rs.normal(size=N)
+    a = rs.normal(0, 1, size=G)
+    b = rs.normal(1, 0.5, size=G)
+    gi = numpy.repeat(numpy.arange(G), R)
+    eta = a[gi] + b[gi] * x
+    y = (rs.random_sample(N) < 1 / (1 + numpy.exp(-eta))).astype(float)
+    return x, y, ("a", "b"), {"a": [-2, 2], "b": [-1, 3]}
+
+
 def schedule(args):
     """A (warmup+steps)-step slice of C3's schedule: burn = half the iterations, thin 10."""
     total = (args.warmup + args.steps) * args.iters_per_step
@@ -110,8 +124,12 @@ def _cpuChainWorker(job):
     spent in the iteration loop (start-up excluded, like the GPU arm)."""
     chain, nIter, G, R, K = job
     from oracle import posterior_oracle as po
-    X, y, names, ranges = makeWorkload(G, R, K)
-    obj = po.LinearRegressionObjective(X, y)
+    if K == 0:                                   # C5: Bernoulli-logit
+        x, y, names, ranges = makeLogitWorkload(G, R)
+        obj = po.BernoulliLogitObjective(x, y)
+    else:
+        X, y, names, ranges = makeWorkload(G, R, K)
+        obj = po.LinearRegressionObjective(X, y)
     oc = po.OracleChain(chain, chain, max(nIter, 10), max(nIter, 10) // 2, names, G, R, "partial",
                         obj, None, False, ranges)
     oc.nIter = nIter
@@ -149,7 +167,7 @@ def runReference(args):
         cpuBaseline(args, cores, iters)     # includes process start-up and data generation per step
     dt = time.perf_counter() - t0
     value = cores * iters * args.steps / dt
-    P, N = args.coef + 1, args.groups * args.obs
+    P, N = (args.coef + 1 if args.coef else 2), args.groups * args.obs
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -164,12 +182,14 @@ def runReference(args):
 
 
 def workloadConfig(args, chains):
-    return {"workload": "C3: hierarchical linear regression, partial pooling, %d groups x %d obs x %d "
-                        "coefficients (+sigma)" % (args.groups, args.obs, args.coef),
+    name = ("C3: hierarchical linear regression, partial pooling, %d groups x %d obs x %d coefficients (+sigma)"
+            % (args.groups, args.obs, args.coef)) if args.coef else \
+           ("C5: hierarchical Bernoulli-logit, partial pooling, %d groups x %d trials, 2 parameters" % (args.groups, args.obs))
+    return {"workload": name,
             "chains_per_gpu": chains, "iters_per_step": args.iters_per_step,
             "schedule": "burn = first half of the run (tune every 100), thin %d after" % args.thin,
             "l2": "chain state + sample write-back exceed L2 (%.0f MB touched per iteration)"
-                  % (chains * args.groups * (args.coef + 1) * 28 / 1e6)}
+                  % (chains * args.groups * ((args.coef + 1) if args.coef else 2) * 28 / 1e6)}
 
 
 def roofline(args, tensorCore, sweepMs, chains, peakFp32, peakTf32, peakMufu):
@@ -181,6 +201,14 @@ def roofline(args, tensorCore, sweepMs, chains, peakFp32, peakTf32, peakMufu):
     observations rounded up to 16 -- and that pipe is the one that binds once latencies are hidden,
     so achieved = those TF32 flop over the launch time against the pipe's measured MMA rate."""
     G, R, K = args.groups, args.obs, args.coef
+    if K == 0:      # C5: 2 MUFU (ex2, lg2) + 6 FP32 flop per evaluation (SURVEY.md section 8d): the MUFU pipe binds
+        evals = 2.0 * G * R * chains
+        ops = 2.0 * evals / (sweepMs * 1e-3)
+        return {"bound": "mufu", "kernel": "sweep_kernel<Logit,4,float>", "achieved": ops / 1e9, "peak": peakMufu / 1e9,
+                "unit": "Gop/s", "frac": ops / peakMufu, "mufu_per_eval": 2.0, "traffic": None,
+                "fp32_pipe_peak_tflops": peakFp32 / 1e12,
+                "peak_source": "MUFU pipe limit measured in this run by an ex2-only microbenchmark (mcmcn_peak_mufu); "
+                               "nominal 148 SM x 16 lanes x 1.965 GHz = 4653"}
     P, N = K + 1, G * R
     algFlops = FLOP_PER_EVAL * P * N * chains
     algTflops = algFlops / (sweepMs * 1e-3) / 1e12
@@ -226,10 +254,15 @@ def runGpu(args):
     dev = torch.device("cuda", local)
 
     G, R, K = args.groups, args.obs, args.coef
-    P, N = K + 1, G * R
+    N = G * R
     chains = args.chains_per_gpu
-    X, y, names, ranges = makeWorkload(G, R, K)
-    obj = Objective.linear_regression(X, y, args.precision)
+    if K == 0:
+        x, y, names, ranges = makeLogitWorkload(G, R)
+        obj = Objective.bernoulli_logit(x, y, args.precision)
+    else:
+        X, y, names, ranges = makeWorkload(G, R, K)
+        obj = Objective.linear_regression(X, y, args.precision)
+    P = len(names)
     eng = Engine(obj, G, R, "partial", chains, chainId0=rank * chains, seed=args.seed)
     eng.initialise(names, ranges)
     total, burn, thin = schedule(args)
@@ -339,6 +372,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c5"],
+                    help="c3 (default, the config BASELINE.json's metric is quoted on) or c5 (Bernoulli-logit: "
+                         "10,000 groups x 50 trials, 4,096 chains; sets --groups/--obs/--coef/--chains-per-gpu)")
     ap.add_argument("--chains-per-gpu", type=int, default=1024)
     ap.add_argument("--groups", type=int, default=1024)
     ap.add_argument("--obs", type=int, default=200)
@@ -356,6 +392,9 @@ def main():
     ap.add_argument("--traffic-pipe", type=float, default=204.2e6,
                     help="same for the FP32-pipe kernel (profiles/r1_sweep_kernel_ncu_summary.txt)")
     args = ap.parse_args()
+    if args.workload == "c5":
+        args.groups, args.obs, args.coef, args.chains_per_gpu = 10000, 50, 0, 4096
+        args.iters_per_step, args.thin = min(args.iters_per_step, 20), max(args.thin, 20)
     if args.warmup < 3 and args.impl == "b200":
         print("warning: the timing rules ask for >= 3 warm-up steps", file=sys.stderr)
     if args.impl == "reference":

@@ -411,19 +411,26 @@ struct Logit {
     __device__ static __forceinline__ void accumulate(const T* __restrict__ blk, int nobs, const double*,
                                                       const Work<C, T>& w, double (&acc)[C], const ObsCtx&) {
         const int nq = nobs >> 2;
-        for (int q = 0; q < nq; ++q) {
-            T x4[4], y4[4];
-            Vec4<T>::load(blk + (size_t)q * UNIT, x4);
-            Vec4<T>::load(blk + (size_t)q * UNIT + 4, y4);
+        // FP32 partial sums over 16 observations, then folded into FP64 (the conversion runs on the
+        // same XU pipe as the two MUFU ops per evaluation that bound this objective)
+        for (int q0 = 0; q0 < nq; q0 += 4) {
             T s[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) s[c] = (T)0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int u = 0; u < 4; ++u) {
+                if (q0 + u < nq) {
+                    T x4[4], y4[4];
+                    Vec4<T>::load(blk + (size_t)(q0 + u) * UNIT, x4);
+                    Vec4<T>::load(blk + (size_t)(q0 + u) * UNIT + 4, y4);
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    const T eta = fma_t(w.th[c][1], x4[j], w.th[c][0]);
-                    s[c] += fma_t(y4[j], eta, -softplus_t(eta));
+                    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            const T eta = fma_t(w.th[c][1], x4[j], w.th[c][0]);
+                            s[c] += fma_t(y4[j], eta, -softplus_t(eta));
+                        }
+                    }
                 }
             }
 #pragma unroll
