@@ -330,6 +330,24 @@ def runGpu(args):
     barrier()
     msE2e = e0.elapsed_time(e1)
 
+    # ---- between-chain diagnostics of the rows the e2e pass retained, on the device; with N > 1 the
+    # half-chain moments and per-lag sums cross NVLink in one NCCL all-gather (the path's only exchange)
+    from sampleDiagnosis import convergenceFromStore
+    nKept = len(store.iterations)
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    diag = None
+    if nKept >= 4:
+        barrier()
+        d0.record()
+        rhat, ess = convergenceFromStore(store.tensor, nKept, chains, group=dist.group.WORLD if world > 1 else None)
+        d1.record()
+        barrier()
+        fin = torch.isfinite(ess)
+        diag = {"rows": nKept, "half_chains": 2 * chains * world, "keys": int(ess.numel()),
+                "min_ess": float(ess[fin].min()) if bool(fin.any()) else None,
+                "max_rhat": float(rhat[torch.isfinite(rhat)].max()),
+                "diag_ms": d0.elapsed_time(d1)}
+
     t = torch.tensor([ms, msE2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -356,6 +374,12 @@ def runGpu(args):
                               "step_kernel_share": sweepMs * timing[3] / ms},
                 "roofline": roofline(args, tensorCore, sweepMs, chains, peakFlops, peakTf32.value, mufu.value),
                 "clocks": clocks}
+        if diag is not None and diag["min_ess"] is not None:
+            samplingS = (args.warmup + args.steps) * msE2e / args.steps * 1e-3     # every iteration it took to get the rows
+            diag["min_ess_per_sec"] = diag["min_ess"] / samplingS
+            diag["note"] = "min over all keys of the effective sample size (sampleDiagnosis.py:232-255) of the retained " \
+                           "rows of all chains / wall time of burn-in + sampling at the e2e rate"
+        line["min_ess"] = diag
         if world == 1 and not args.no_cpu_baseline:
             v, dt = cpuBaseline(args, 1, args.cpu_iters)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",

@@ -111,6 +111,37 @@ def mergeShards(mean, var, vario, group):
     return mean, var, total
 
 
+def convergenceFromStore(storeTensor, nRows, nChains, group=None):
+    """R-hat and effective sample size of every column of a device-resident sample store
+    ([rows][ncol][S], chain fastest; engine.SampleStore) without leaving the GPU: the same
+    kernels and formulas as Diagnostic (:158-255), the rows split into first / second half per
+    chain (:118-156).  With ``group`` every rank holds a shard of the chains and the half-chain
+    moments and per-lag sums are exchanged by one NCCL all-gather (mergeShards).
+    Returns (rhat[ncol], ess[ncol]) as device tensors."""
+    n = int(nRows) // 2
+    if n < 2:
+        raise ValueError("need at least 4 retained rows per chain")
+    ncol = storeTensor.shape[1]
+    dev = storeTensor.device
+    x = storeTensor[:2 * n, :, :nChains].permute(1, 2, 0).to(torch.float64)        # [ncol][nC][2n]
+    x = x.reshape(ncol, 2 * nChains, n).contiguous()                               # half-chains: chain c -> 2c, 2c+1
+    st = _stream(dev)
+    mL = 2 * nChains
+    mean = torch.empty((ncol, mL), dtype=torch.float64, device=dev)
+    var = torch.empty((ncol, mL), dtype=torch.float64, device=dev)
+    nat.call("mcmcn_diag_moments", _ptr(x), ncol, mL, n, _ptr(mean), _ptr(var), st)
+    vario = torch.empty((ncol, n), dtype=torch.float64, device=dev)
+    nat.call("mcmcn_diag_variogram", _ptr(x), ncol, mL, n, _ptr(vario), st)
+    if group is not None:
+        mean, var, vario = mergeShards(mean, var, vario, group)
+    m = mean.shape[1]
+    rh = torch.empty((ncol, 4), dtype=torch.float64, device=dev)
+    nat.call("mcmcn_diag_rhat", _ptr(mean), _ptr(var), ncol, m, n, _ptr(rh), st)
+    ess = torch.empty((ncol,), dtype=torch.float64, device=dev)
+    nat.call("mcmcn_diag_ess", _ptr(vario), _ptr(rh), ncol, m, n, None, _ptr(ess), st)
+    return rh[:, 3].contiguous(), ess
+
+
 def chainRange(nChains, rank, world):
     """Contiguous global chain ids [lo, hi) of a rank."""
     return (nChains * rank) // world, (nChains * (rank + 1)) // world

@@ -279,3 +279,20 @@ def test_user_objective_compile_error_is_reported():
     with pytest.raises(RuntimeError, match="failed to compile"):
         Objective.from_source("__device__ mcmc_real mcmc_obj_loglik(const mcmc_real* t) { return nope; }",
                               2, numpy.zeros((4, 1)))
+
+
+def test_convergence_from_device_store_matches_diagnostic():
+    """convergenceFromStore (R-hat / ESS straight from the device-resident sample store, used by
+    bench.py's min-ESS figure) against Diagnostic on the same draws (north star: 1e-10)."""
+    import torch
+    import sampleDiagnosis as sd
+    rs = numpy.random.RandomState(3)
+    nChains, rows, ncol, S = 5, 40, 7, 32
+    draws = numpy.cumsum(rs.normal(size=(nChains, rows, ncol)), axis=1) * 0.1 + rs.normal(size=(nChains, 1, ncol))
+    store = torch.zeros((rows + 3, ncol, S), dtype=torch.float64, device="cuda")
+    store[:rows, :, :nChains] = torch.from_numpy(numpy.transpose(draws, (1, 2, 0))).cuda()
+    rhat, ess = sd.convergenceFromStore(store, rows, nChains)
+    keys = ["k[%03d]" % i for i in range(ncol)]
+    d = sd.Diagnostic(samples=draws, keys=keys)
+    numpy.testing.assert_allclose(rhat.cpu().numpy(), [d.rhat[k] for k in keys], rtol=1e-10)
+    numpy.testing.assert_allclose(ess.cpu().numpy(), [d.effectiveN[k] for k in keys], rtol=1e-10)
