@@ -173,45 +173,53 @@ struct TcInputs {
 // (w + 0.5) * 2^-32 in (0, 1).  `stash` carries the second pair to the odd sweep.
 struct TcStash { double z, u; };
 
+// (w + 0.5) * 2^-32 in (0, 1) from a 32-bit word without an integer-to-double conversion: the
+// word fills the top mantissa bits of a double in [1, 2), then one exact subtraction.
+__device__ __forceinline__ double tc_uniform32(unsigned w) {
+    return __hiloint2double((int)(0x3FF00000u | (w >> 12)), (int)((w << 20) | 0x80000u)) - 1.0;
+}
+
+// `at` = element index of (name p, group g, this chain) in the [P][G][S] arrays, `hy` = p * S + chain
+// in the [5][P][S] hyper-parameters, `bb` = g * K + p in bbar; the caller bumps them per sweep.
+// State loads and random numbers are separate so that they can sit behind different MMAs.
 template <bool GENERAL>
-__device__ __forceinline__ TcInputs tc_fetch(const SweepArgs& a, int p, int g, int chl, bool partial, bool replay, bool override_lp,
-                                             TcStash& stash) {
+__device__ __forceinline__ void tc_fetch_state(TcInputs& o, const SweepArgs& a, int p, size_t at, size_t hy, size_t bb,
+                                               bool partial, bool override_lp) {
     const int P = a.P;
-    const size_t S = (size_t)a.S;
-    const size_t row = ((size_t)p * a.G + g) * S;
-    TcInputs o;
-    o.cur = a.theta[row + chl];
-    o.sc = a.scale[row + chl];
+    const size_t PS = (size_t)P * (size_t)a.S;
+    o.cur = a.theta[at];
+    o.sc = a.scale[at];
     o.h_mu = o.h_lsd = o.h_isd = o.lp_cur = 0.0;
-    o.bbar = p < P - 1 ? a.obj_const[(size_t)g * (P - 1) + p] : 0.0;
+    o.bbar = p < P - 1 ? a.obj_const[bb] : 0.0;
     if (partial) {
-        o.h_mu = a.hyper[((size_t)0 * P + p) * S + chl];
-        o.h_lsd = a.hyper[((size_t)3 * P + p) * S + chl];
-        o.h_isd = a.hyper[((size_t)4 * P + p) * S + chl];
-        if (GENERAL && override_lp) o.lp_cur = a.lprior[row + chl];
+        o.h_mu = a.hyper[hy];
+        o.h_lsd = a.hyper[3 * PS + hy];
+        o.h_isd = a.hyper[4 * PS + hy];
+        if (GENERAL && override_lp) o.lp_cur = a.lprior[at];
     } else {
-        o.lp_cur = a.lprior[row + chl];
+        o.lp_cur = a.lprior[at];
     }
+}
+template <bool GENERAL>
+__device__ __forceinline__ void tc_fetch_random(TcInputs& o, const SweepArgs& a, int p, int g, int chl, size_t at, bool replay,
+                                                TcStash& stash) {
     if (GENERAL && replay) {
-        o.z = a.tape_z[row + chl];
-        o.u = a.tape_u[row + chl];
+        o.z = a.tape_z[at];
+        o.u = a.tape_u[at];
+    } else if ((p & 1) == 0) {
+        const uint4 rnd = philox_draw(a.chain_id0 + chl, a.seed, a.iter, MCMCN_STREAM_SWEEP, (unsigned)((p >> 1) * a.G + g), 1u);
+        const float u1 = (float)((rnd.x >> 8) + 1u) * 5.9604644775390625e-8f;   // (0, 1]
+        const float u2 = (float)(rnd.y >> 8) * 5.9604644775390625e-8f;          // [0, 1)
+        float r;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));
+        o.z = (double)(r * __cosf(6.283185307179586f * u2));
+        stash.z = (double)(r * __sinf(6.283185307179586f * u2));
+        o.u = tc_uniform32(rnd.z);
+        stash.u = tc_uniform32(rnd.w);
     } else {
-        if ((p & 1) == 0) {
-            const uint4 rnd = philox_draw(a.chain_id0 + chl, a.seed, a.iter, MCMCN_STREAM_SWEEP, (unsigned)((p >> 1) * a.G + g), 1u);
-            const float u1 = (float)((rnd.x >> 8) + 1u) * 5.9604644775390625e-8f;   // (0, 1]
-            const float u2 = (float)(rnd.y >> 8) * 5.9604644775390625e-8f;          // [0, 1)
-            float r;
-            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));
-            o.z = (double)(r * __cosf(6.283185307179586f * u2));
-            stash.z = (double)(r * __sinf(6.283185307179586f * u2));
-            o.u = ((double)rnd.z + 0.5) * 2.3283064365386963e-10;
-            stash.u = ((double)rnd.w + 0.5) * 2.3283064365386963e-10;
-        } else {
-            o.z = stash.z;
-            o.u = stash.u;
-        }
+        o.z = stash.z;
+        o.u = stash.u;
     }
-    return o;
 }
 
 // CTA-wide rendezvous before an MMA issue: every lane's tensor-memory traffic (tcgen05.st of the
@@ -221,8 +229,14 @@ __device__ __forceinline__ TcInputs tc_fetch(const SweepArgs& a, int p, int g, i
 __device__ __forceinline__ bool tc_rendezvous_issuer() {
     tc_fence_before();
     __syncthreads();
-    if (threadIdx.x == 0) tc_fence_after();
-    return threadIdx.x == 0;
+    bool issuer = false;
+    if (threadIdx.x < 32) {                   // warp-uniform branch, then one elected lane: lets ptxas keep the
+        unsigned pred;                        // MMA operands in uniform registers without a per-instruction loop
+        asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+        issuer = pred != 0;
+        if (issuer) tc_fence_after();
+    }
+    return issuer;
 }
 
 // grid = (group ranges, chain blocks of 128); block = 128 threads; dynamic shared memory =
@@ -298,7 +312,11 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
         const unsigned stage = stage0 + (unsigned)s * (unsigned)a.tc_stage_bytes;
         const double* bbar = a.obj_const + (size_t)g * K;
 
-        TcInputs in = tc_fetch<GENERAL>(a, 0, g, chl, partial, replay, override_lp, stash);
+        const size_t GS = (size_t)a.G * S;
+        size_t at = (size_t)g * S + chl, hy = (size_t)chl, bb = (size_t)g * K;   // sweep 0; bumped by GS / S / 1 per sweep
+        TcInputs in;
+        tc_fetch_state<GENERAL>(in, a, 0, at, hy, bb, partial, override_lp);
+        tc_fetch_random<GENERAL>(in, a, 0, g, chl, at, replay, stash);
         if (g + 1 < g1) {                                              // next group's state: DRAM -> L2 meanwhile
             for (int k = 0; k < P; ++k)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(a.theta + ((size_t)k * a.G + g + 1) * S + chl));
@@ -331,11 +349,11 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
         tma_phase ^= 1u << s;
 
 #pragma unroll 1
-        for (int p = 0; p < P; ++p) {
-            const size_t at = ((size_t)p * a.G + g) * S + chl;
+        for (int p = 0; p < P; ++p, at += GS, hy += S, ++bb) {
             const bool is_sigma = p == K;
             // proposal and log-priors (pure functions of state known before the sweep; the reference
-            // evaluates them after the likelihood, :335, :331)
+            // evaluates them after the likelihood, :335, :331).  (Moving the priors or the random numbers
+            // behind the MMAs instead measured 7-10 % slower, twice.)
             const double prop = __dadd_rn(in.cur, __dmul_rn(in.sc, in.z));     // numpy.random.normal(value, sd), :304-306
             double lp_prop, lp_cur;
             if (partial) {
@@ -366,8 +384,13 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
             }
             tmem_wait_st();
             if (tc_rendezvous_issuer()) tc_issue_chunk(tbase, stage, ones, np, 0, mb_mma);
-            // while the tensor core works: state and random numbers of the next sweep
-            if (p + 1 < P) in = tc_fetch<GENERAL>(a, p + 1, g, chl, partial, replay, override_lp, stash);
+            // while the tensor core works: state and random numbers of the next sweep.  (Drawing the
+            // random numbers inside the read-back code instead, to fill its tensor-memory latency, cost
+            // registers and measured 8 % slower.)
+            if (p + 1 < P) {
+                tc_fetch_state<GENERAL>(in, a, p + 1, at + GS, hy + S, bb + 1, partial, override_lp);
+                tc_fetch_random<GENERAL>(in, a, p + 1, g, chl, at + GS, replay, stash);
+            }
 
             double acc = 0.0;
             for (int c = 0; c < nchunks; ++c) {
