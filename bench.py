@@ -315,6 +315,12 @@ def runGpu(args):
     h2d = pinData.numel() * pinData.element_size()
     d2h = 0
     barrier()
+    # the device->host reads run on a second stream, so the rows of step k travel while step k + 1
+    # computes; every copy is finished before the closing event (the main stream waits for the copy stream)
+    main = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(dev)
+    hyperSnap = torch.empty_like(eng.hyper)          # the step's hyper-parameters, frozen before the next step overwrites them
+    snapFree = torch.cuda.Event()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(args.steps):
@@ -322,10 +328,17 @@ def runGpu(args):
         r0 = len(store.iterations)
         eng.run((args.warmup + k) * ips, ips, burn, thin, store=store)
         r1 = len(store.iterations)
-        if r1 > r0:
-            pinRows[:r1 - r0].copy_(store.tensor[r0:r1], non_blocking=True)
-        pinHyper.copy_(eng.hyper, non_blocking=True)
+        if k:
+            main.wait_event(snapFree)
+        hyperSnap.copy_(eng.hyper, non_blocking=True)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            if r1 > r0:                              # retained rows are append-only: nothing overwrites them
+                pinRows[:r1 - r0].copy_(store.tensor[r0:r1], non_blocking=True)
+            pinHyper.copy_(hyperSnap, non_blocking=True)
+            snapFree.record(side)
         d2h += (r1 - r0) * rowBytes + pinHyper.numel() * 8
+    main.wait_stream(side)
     e1.record()
     barrier()
     msE2e = e0.elapsed_time(e1)

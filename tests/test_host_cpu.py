@@ -114,6 +114,43 @@ def test_regression_packing_is_the_same_residual():
         assert list(nobs) == nResp and off[-1] == data.size
 
 
+def test_tensor_core_operand_blocks_are_an_exact_3xtf32_split():
+    """mcmcn_model.tc_data (include/mcmcn.h): per group [X_hi | X_lo | NE] in the K-major core-matrix
+    layout; every part must be exact in TF32 (13 zero low bits) and the parts must add up to the
+    same FP32 values the FP32-pipe block holds, so both step kernels evaluate the same residual."""
+    from objectives import Objective
+    rs = numpy.random.RandomState(1)
+    nResp = [5, 17, 1, 200, 16]
+    N, K = sum(nResp), 5
+    X, y = rs.normal(size=(N, K)), 300 + rs.normal(size=N)
+    obj = Objective.linear_regression(X, y, "fp32")
+    data, off, nobs, bbar = obj.pack(nResp)
+    tc, tcOff = obj.tcData, obj.tcGroupOff
+    assert tc.dtype == numpy.float32 and len(tcOff) == len(nResp) + 1
+    assert numpy.all((tc.view(numpy.uint32) & 0x1FFF) == 0)              # exact in TF32
+    bbar = bbar.reshape(len(nResp), K)
+    start = 0
+    for g, r in enumerate(nResp):
+        n = max(16, (r + 15) // 16 * 16)
+        blk = tc[tcOff[g]:tcOff[g + 1]]
+        assert blk.size == 24 * n
+
+        def unslab(a):                                                   # core-matrix order -> [n][8]
+            return a.reshape(n // 8, 2, 8, 4).transpose(0, 2, 1, 3).reshape(n, 8)
+        xhi, xlo, ne = unslab(blk[:8 * n]), unslab(blk[8 * n:16 * n]), unslab(blk[16 * n:])
+        x32 = numpy.zeros((n, 8), dtype=numpy.float32)
+        x32[:r, :K] = X[start:start + r]
+        assert numpy.all(numpy.abs((xhi.astype(float) + xlo) - x32) <= numpy.abs(x32) * 2.0 ** -21)
+        ne32 = numpy.zeros(n, dtype=numpy.float32)
+        ne32[:r] = X[start:start + r] @ bbar[g] - y[start:start + r]
+        assert numpy.array_equal(ne[:, 0].astype(float) + ne[:, 1] + ne[:, 2], ne32.astype(float))   # three parts: exact
+        assert numpy.all(ne[:, 3:] == 0) and numpy.all(xhi[r:] == 0) and numpy.all(xhi[:, K:] == 0)
+        # element (n, k) of a slab sits at float index (n/8)*64 + (k/4)*32 + (n%8)*4 + (k%4)
+        for (i, k) in ((0, 0), (r - 1, K - 1), (9 % n, 4)):
+            assert blk[(i // 8) * 64 + (k // 4) * 32 + (i % 8) * 4 + (k % 4)] == xhi[i, k]
+        start += r
+
+
 def test_prior_mapping():
     from engine import priorFromScipy
     pr = priorFromScipy(scipy.stats.gamma(10))
