@@ -40,17 +40,70 @@ def _stream(dev):
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
-def _sortedMedianHdi(x, hdi_p):
-    """x: device double [n_keys][len] (destroyed: sorted in place).  Returns host [n_keys][3]
+def _sortedMedianHdiDevice(x, hdi_p):
+    """x: device double [n_keys][len] (destroyed: sorted in place).  Returns device [n_keys][3]
     = median, HDI lower, HDI upper (computeHpdInterval, :766-776)."""
     dev = x.device
     nKeys, length = x.shape
     prob = hdi_p / 100.
     gap = max(1, min(length - 1, round(length * prob)))          # Python banker's rounding
     out = torch.empty((nKeys, 3), dtype=torch.float64, device=dev)
-    nat.call("mcmcn_diag_sort_keys", _ptr(x), nKeys, length, _stream(dev))
-    nat.call("mcmcn_diag_median_hdi", _ptr(x), nKeys, length, gap, _ptr(out), _stream(dev))
-    return out.cpu().numpy()
+    if nKeys:
+        nat.call("mcmcn_diag_sort_keys", _ptr(x), nKeys, length, _stream(dev))
+        nat.call("mcmcn_diag_median_hdi", _ptr(x), nKeys, length, gap, _ptr(out), _stream(dev))
+    return out
+
+
+def _sortedMedianHdi(x, hdi_p):
+    return _sortedMedianHdiDevice(x, hdi_p).cpu().numpy()
+
+
+def keyRange(nKeys, rank, world):
+    """Contiguous slice [lo, hi) of the keys a rank owns in the key-partitioned exchange."""
+    return (nKeys * rank) // world, (nKeys * (rank + 1)) // world
+
+
+def exchangeByKey(local, group):
+    """Key-partitioned exchange for the pooled order statistics:
+    ``local`` is this rank's [n_keys][len] draws; rank r becomes the owner of keys keyRange(r)
+    and receives every rank's draws of those keys, concatenated in rank (= chain) order:
+    returns [keys_owned][world * len].  One all-to-all over NVLink with NCCL; backends without
+    all-to-all (gloo, used by the CPU tests) run the same exchange as one gather per owner."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    nKeys, length = local.shape
+    send = [local[slice(*keyRange(nKeys, r, world))].contiguous() for r in range(world)]
+    lo, hi = keyRange(nKeys, rank, world)
+    recv = [torch.empty((hi - lo, length), dtype=local.dtype, device=local.device) for _ in range(world)]
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all(recv, send, group=group)
+    else:
+        for r in range(world):
+            dist.gather(send[r], gather_list=recv if r == rank else None, dst=dist.get_global_rank(group, r) if group is not None else r,
+                        group=group)
+    return torch.cat(recv, dim=1).contiguous()
+
+
+def pooledMedianHdi(local, hdi_p, group, keySlab=2048):
+    """numpy.median and the HDI (:419-427, :766-776) of every key over ALL ranks' draws without
+    any rank ever holding all draws of all keys: keys go through exchangeByKey in slabs, their
+    owners sort them, and the [n_keys][3] results are all-gathered.  Returns device [n_keys][3]."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    nKeys = local.shape[0]
+    out = torch.empty((nKeys, 3), dtype=torch.float64, device=local.device)
+    for k0 in range(0, nKeys, keySlab):
+        k1 = min(nKeys, k0 + keySlab)
+        mine = _sortedMedianHdiDevice(exchangeByKey(local[k0:k1], group), hdi_p)     # [keys owned in this slab][3]
+        most = max(keyRange(k1 - k0, r, world)[1] - keyRange(k1 - k0, r, world)[0] for r in range(world))
+        pad = torch.zeros((most, 3), dtype=torch.float64, device=local.device)
+        pad[:mine.shape[0]] = mine
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad, group=group)
+        for r in range(world):
+            lo, hi = keyRange(k1 - k0, r, world)
+            out[k0 + lo:k0 + hi] = parts[r][:hi - lo]
+    return out
 
 
 def computeHpdInterval(samples, hdi_p=95):
@@ -206,9 +259,10 @@ class Diagnostic(object):
         rho = torch.empty((nKeys, n), dtype=f64, device=dev)
         nat.call("mcmcn_diag_ess", _ptr(vario), _ptr(rh), nKeys, m, n, _ptr(rho), _ptr(ess), st)
         pooled = self._x.reshape(nKeys, mL * n)
-        if self._group is not None:
-            pooled = gatherShards(pooled.reshape(nKeys, mL, n), self._group).reshape(nKeys, m * n)
-        mh = _sortedMedianHdi(pooled.clone(), self._hdiP)
+        if self._group is not None:       # key-partitioned all-to-all: no rank holds every key's pooled draws
+            mh = pooledMedianHdi(pooled, self._hdiP, self._group).cpu().numpy()
+        else:
+            mh = _sortedMedianHdi(pooled.clone(), self._hdiP)
         rh_h, ess_h = rh.cpu().numpy(), ess.cpu().numpy()
         self._rhoArr = rho.cpu().numpy()
         k = self._keys

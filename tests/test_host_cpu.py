@@ -231,6 +231,10 @@ def _gloo_worker(rank, world, port, tmp):
     gm, gv, gvario = sd.mergeShards(mean, var, vario, dist.group.WORLD)
     numpy.save(os.path.join(tmp, "merged.%d.npy" % rank),
                numpy.concatenate([gm.numpy().ravel(), gv.numpy().ravel(), gvario.numpy().ravel()]))
+    # key-partitioned exchange of the pooled draws (median / HDI across ranks)
+    pooled = torch.from_numpy(numpy.ascontiguousarray(mine.reshape(5, -1)))
+    owned = sd.exchangeByKey(pooled, dist.group.WORLD)
+    numpy.save(os.path.join(tmp, "owned.%d.npy" % rank), owned.numpy())
     dist.destroy_process_group()
 
 
@@ -250,6 +254,11 @@ def test_shard_merge_over_gloo_world_size_2(tmp_path):
     numpy.testing.assert_array_equal(a[:60], mean.ravel())
     numpy.testing.assert_array_equal(a[60:120], var.ravel())
     numpy.testing.assert_allclose(a[120:], vario.ravel(), rtol=1e-13)
+    # exchangeByKey: rank r owns keys keyRange(5, r, 2) and holds ALL chains' draws of them, chain order
+    import sampleDiagnosis as sd
+    for r in range(2):
+        lo, hi = sd.keyRange(5, r, 2)
+        numpy.testing.assert_array_equal(numpy.load(tmp_path / ("owned.%d.npy" % r)), x[lo:hi].reshape(hi - lo, -1))
 
 
 def test_chain_ranges_partition_the_chains():

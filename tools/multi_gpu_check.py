@@ -7,8 +7,8 @@
 1. samplePosterior with the chains sharded over the ranks writes, chain for chain, the same
    sample files as a single-GPU run (Philox and the start-state streams are keyed by the global
    chain id, so results do not depend on the GPU count).
-2. Diagnostic over the sharded chains (all-gather of per-half-chain summaries over NCCL) equals
-   Diagnostic over all chains in one process.
+2. Diagnostic over the sharded chains (all-gather of per-half-chain summaries over NCCL; pooled
+   median / HDI through a key-partitioned all-to-all) equals Diagnostic over all chains in one process.
 Prints MULTI_GPU_OK on rank 0."""
 import os
 import sys
@@ -42,7 +42,7 @@ def main():
     keys, allSamples, chains = sd.loadSamples(out + "/multi/sample/")
     mine = allSamples[lo:hi]
     dShard = sd.Diagnostic(samples=mine, keys=keys, group=dist.group.WORLD)
-    rhat, ess, med = dShard.rhat, dShard.effectiveN, dShard.median
+    rhat, ess, med, hdi = dShard.rhat, dShard.effectiveN, dShard.median, dShard.hdi
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
@@ -57,7 +57,7 @@ def main():
         for k in keys:
             numpy.testing.assert_allclose(rhat[k], dAll.rhat[k], rtol=1e-12)
             numpy.testing.assert_allclose(ess[k], dAll.effectiveN[k], rtol=1e-11)
-            assert med[k] == dAll.median[k]
+            assert med[k] == dAll.median[k] and hdi[k] == dAll.hdi[k]     # key-partitioned all-to-all: exact
         print("MULTI_GPU_OK world=%d chains=%d keys=%d" % (world, nChains, len(keys)))
 
 
