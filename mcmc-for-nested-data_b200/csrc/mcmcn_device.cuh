@@ -927,10 +927,27 @@ __global__ void __launch_bounds__(256) eval_kernel(const SweepArgs a) {
 
 // Pointwise log-likelihood of the current state (saveLogLikelihood, :656-659, :907-909).
 // Not a hot path: reads the blocks straight from global memory.  grid = (G, chain blocks of 128).
+// The index of the group's first observation is the sum of the group sizes before it, which
+// each block adds up itself (`obs_off` may be NULL), so the call needs no scratch memory.
 template <class Obj, typename T>
 __global__ void pointwise_kernel(const SweepArgs a, const long long* obs_off, double* out) {
     constexpr int P = Obj::P;
+    __shared__ long long part[128];
     const int g = blockIdx.x;
+    long long o0;
+    if (obs_off) {
+        o0 = obs_off[g];
+    } else {
+        long long s = 0;
+        for (int h = threadIdx.x; h < g; h += blockDim.x) s += a.group_nobs[h];
+        part[threadIdx.x] = s;
+        __syncthreads();
+        for (int w = 64; w > 0; w >>= 1) {
+            if ((int)threadIdx.x < w && threadIdx.x + w < blockDim.x) part[threadIdx.x] += part[threadIdx.x + w];
+            __syncthreads();
+        }
+        o0 = part[0];
+    }
     const int ch = blockIdx.y * blockDim.x + threadIdx.x;
     if (ch >= a.n_chains) return;
     const size_t S = (size_t)a.S;
@@ -939,7 +956,6 @@ __global__ void pointwise_kernel(const SweepArgs a, const long long* obs_off, do
     for (int p = 0; p < P; ++p) th[p] = Obj::template local<T>(p, a.theta[((size_t)p * a.G + g) * S + ch], a.obj_const, g);
     const T* blk = reinterpret_cast<const T*>(a.data) + a.group_off[g];
     const int R = a.group_nobs[g];
-    const long long o0 = obs_off[g];
     for (int i = 0; i < R; ++i)
         out[(size_t)(o0 + i) * S + ch] = Obj::template pointwise<T>(blk + Obj::HDR, i, a.obj_const, th, g, blk);
 }

@@ -361,28 +361,11 @@ int mcmcn_pointwise_loglik(const mcmcn_model* m, const mcmcn_state* s, double* o
     if (!out) { set_error("null output"); return MCMCN_ERR_INVALID; }
     SweepArgs a;
     fill_args(a, ks, m, s);
-    // observation offsets per group (device scratch, built from the host table)
-    const int G = m->n_groups;
-    long long* obs_off_h = new long long[G + 1];
-    int* nobs_h = new int[G];
-    cudaError_t e = cudaMemcpy(nobs_h, m->group_nobs, sizeof(int) * G, cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) { delete[] obs_off_h; delete[] nobs_h; set_error("cuda: %s", cudaGetErrorString(e)); return MCMCN_ERR_CUDA; }
-    obs_off_h[0] = 0;
-    for (int g = 0; g < G; ++g) obs_off_h[g + 1] = obs_off_h[g] + nobs_h[g];
-    long long* obs_off_d = nullptr;
-    e = cudaMalloc(&obs_off_d, sizeof(long long) * (G + 1));
-    if (e == cudaSuccess) e = cudaMemcpy(obs_off_d, obs_off_h, sizeof(long long) * (G + 1), cudaMemcpyHostToDevice);
-    delete[] obs_off_h;
-    delete[] nobs_h;
-    if (e != cudaSuccess) { cudaFree(obs_off_d); set_error("cuda: %s", cudaGetErrorString(e)); return MCMCN_ERR_CUDA; }
-    const dim3 grid((unsigned)G, (unsigned)((s->n_chains + 127) / 128), 1);
-    {
-        void* args[] = {&a, &obs_off_d, &out};
-        e = cudaLaunchKernel((const void*)ks->pointwise, grid, dim3(128, 1, 1), args, 0, (cudaStream_t)stream_);
-    }
-    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream_);
-    cudaFree(obs_off_d);
-    if (e != cudaSuccess) { set_error("cuda: %s", cudaGetErrorString(e)); return MCMCN_ERR_CUDA; }
+    // the kernel derives each group's first observation index itself: no scratch, no synchronisation
+    const dim3 grid((unsigned)m->n_groups, (unsigned)((s->n_chains + 127) / 128), 1);
+    const long long* obs_off = nullptr;
+    void* args[] = {&a, &obs_off, &out};
+    CK(cudaLaunchKernel((const void*)ks->pointwise, grid, dim3(128, 1, 1), args, 0, (cudaStream_t)stream_));
     return MCMCN_OK;
 }
 
