@@ -166,6 +166,13 @@ def smokeCheck(verbose=False):
     torch.cuda.synchronize()
     st = eng.getState()
     assert numpy.isfinite(st["theta"]).all() and numpy.isfinite(st["ll"]).all()
+    # the bench shape of a group (200 observations x 8 coefficients: two accumulator chunks of the
+    # tcgen05 step kernel), a few groups and chains
+    obj2, names2, nResp2, ranges2 = syntheticRegression(G=3, R=200, K=8)
+    res2 = replay(obj2, names2, 3, nResp2, "partial", None, ranges2, nChains=5, nIter=12, nSamples=6)
+    err2, ties2 = checkReplay(res2, 1e-5, 1e-4)
+    assert res2.engine.usesTensorCore
     if verbose:
-        print("smoke ok: replay max rel log-density error %.3g, %d near-threshold ties" % (err, ties))
-    return err, ties
+        print("smoke ok: replay max rel log-density error %.3g / %.3g (C3 group shape, tcgen05 kernel), "
+              "%d near-threshold ties" % (err, err2, ties + ties2))
+    return max(err, err2), ties + ties2
