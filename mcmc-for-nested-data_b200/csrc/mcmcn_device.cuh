@@ -597,6 +597,7 @@ struct SweepArgs {
     const void* tc_data;
     const long long* tc_group_off;
     int tc_stage_bytes;
+    int tc_stages;                // 2: the next group's block is staged while this one is used; 1: big blocks
 };
 
 // Compile-time specialisation of the step kernel.  F < 0: everything decided at run time (the

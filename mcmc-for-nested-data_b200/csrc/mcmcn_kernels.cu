@@ -27,7 +27,7 @@ void set_error(const char* fmt, ...) {
 static const int kTileCapBytes = 64 * 1024;
 // tcgen05 path (mcmcn_tc.cuh): two TMA stages of one group block each + the 4 KB ones operand; the
 // floor keeps the CTAs at four per SM, which is what their 128 TMEM columns allow
-static const int kTcStageCapBytes = 24 * 1024;
+static const int kTcStageCapBytes = 48 * 1024;       // one stage of up to 48 KB (512 observations) or two of up to 24 KB
 static const int kTcSmemFloorBytes = 48 * 1024;
 static const int kTcCtaSlots = 4 * 148;
 
@@ -130,7 +130,7 @@ static bool tc_eligible(const mcmcn_model* m) {
            m->tc_group_off && m->tc_max_block_floats > 0 && m->tc_max_block_floats * 4 <= kTcStageCapBytes &&
            !getenv("MCMCN_NO_TC");
 }
-static Geometry tc_geometry(const mcmcn_model* m, int n_chains, int* stage_bytes) {
+static Geometry tc_geometry(const mcmcn_model* m, int n_chains, int* stage_bytes, int* stages) {
     Geometry g;
     const int ncb = (n_chains + 127) / 128;
     const long long tasks = (long long)ncb * m->n_groups;
@@ -146,7 +146,8 @@ static Geometry tc_geometry(const mcmcn_model* m, int n_chains, int* stage_bytes
     g.grid = dim3((unsigned)nr, (unsigned)ncb, 1);
     g.block = dim3(128, 1, 1);
     *stage_bytes = (int)((m->tc_max_block_floats * 4 + 1023) & ~1023LL);
-    size_t smem = 2 * (size_t)*stage_bytes + 4096 + 1024;
+    *stages = *stage_bytes <= 24 * 1024 ? 2 : 1;
+    size_t smem = (size_t)*stages * (size_t)*stage_bytes + 4096 + 1024;
     if (smem < (size_t)kTcSmemFloorBytes) smem = kTcSmemFloorBytes;
     g.tile_bytes = g.smem = smem;
     return g;
@@ -215,9 +216,10 @@ int mcmcn_run(const mcmcn_model* m, const mcmcn_state* s, const mcmcn_run_args* 
     // keeps the observation loop spill-free (measured: 1.26 M chain-it/s against 1.15 M for 4 CTAs at
     // 128 registers and 1.10 M for 2 CTAs at 254)
     const bool tc = tc_eligible(m);
-    int tc_stage_bytes = 0;
-    const Geometry g = tc ? tc_geometry(m, s->n_chains, &tc_stage_bytes) : geometry(ks, m, s->n_chains, 4);
+    int tc_stage_bytes = 0, tc_stages = 2;
+    const Geometry g = tc ? tc_geometry(m, s->n_chains, &tc_stage_bytes, &tc_stages) : geometry(ks, m, s->n_chains, 4);
     a.tc_stage_bytes = tc_stage_bytes;
+    a.tc_stages = tc_stages;
     // production variants (pooling mode and burn-in bookkeeping folded at compile time) when
     // there is no tape, no trace and every task fits the tile; the general kernel otherwise
     a.tile_bytes = (int)g.tile_bytes;

@@ -240,7 +240,7 @@ __device__ __forceinline__ bool tc_rendezvous_issuer() {
 }
 
 // grid = (group ranges, chain blocks of 128); block = 128 threads; dynamic shared memory =
-// the constant ones operand + 2 stages of a.tc_stage_bytes (1024-byte aligned).
+// the constant ones operand + a.tc_stages (2, or 1 for big groups) stages of a.tc_stage_bytes (1024-byte aligned).
 template <int F>
 __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const SweepArgs a) {
     constexpr bool GENERAL = F < 0;
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
     };
     if (tid == 0) {
         stage_group(0, g0);
-        if (g0 + 1 < g1) stage_group(1, g0 + 1);
+        if (a.tc_stages > 1 && g0 + 1 < g1) stage_group(1, g0 + 1);
     }
 
     const int ch = blockIdx.y * MCMCN_TC_THREADS + tid;
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
     stash.z = stash.u = 0.0;
 
     for (int g = g0; g < g1; ++g) {
-        const int s = (g - g0) & 1;
+        const int s = a.tc_stages > 1 ? ((g - g0) & 1) : 0;
         const int R = a.group_nobs[g];
         const int np = max(16, (R + 15) & ~15);                        // padded observation count of the block
         const int nchunks = (np + MCMCN_TC_CH - 1) / MCMCN_TC_CH;
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
         }
         if (on) a.ll[(size_t)g * S + chl] = ll_cur;
         // every MMA that read this stage has completed (all threads waited on its mbarrier)
-        if (tid == 0 && g + 2 < g1) stage_group(s, g + 2);
+        if (tid == 0 && g + a.tc_stages < g1) stage_group(s, g + a.tc_stages);
     }
     tmem_wait_st();
     tc_fence_before();

@@ -90,6 +90,7 @@ def test_replay_c3_shape_wide_path(precision, tol, tensorCore, monkeypatch):
     (9, 40, 3, True, "partial", 5),          # ragged groups of 1..79 observations, K < 8
     (4, 112, 8, False, "none", 1),           # exactly one full chunk, fixed priors, a single chain
     (7, 200, 5, False, "partial", 257),      # three chain blocks, the last with one chain
+    (3, 500, 8, False, "partial", 40),       # 48 KB blocks: one TMA stage, five accumulator chunks
 ])
 def test_replay_tensor_core_kernel_shapes(G, R, K, ragged, pooling, nChains):
     """The tcgen05 step kernel over the shapes that change its control flow: number of
