@@ -1060,6 +1060,66 @@ __global__ void __launch_bounds__(32 * NS) hyper_kernel(const HyperArgs a) {
     }
 }
 
+// The same update with ONE read of theta, for many groups (G >= 512), where the previous
+// iteration's mu is a shift c within a few standard errors of the mean: sums of (theta - c) and
+// (theta - c)^2, then  mean = c + S1 / G  and
+//   sum (theta - mu)^2 = (S2 - S1^2 / G) + G (mu - mean)^2     (two non-negative terms).
+// Agrees with the two-pass kernel to 1e-13 relative at C3's shape (tests/test_gpu_dropin.py).
+template <int NS>
+__global__ void __launch_bounds__(32 * NS) hyper_onepass_kernel(const HyperArgs a) {
+    __shared__ double red1[NS][33], red2[NS][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int ch = blockIdx.x * 32 + tx;
+    const int p = blockIdx.y;
+    const bool on = ch < a.n_chains;
+    const size_t S = (size_t)a.S;
+    const double* th = a.theta + ((size_t)p * a.G) * S + ch;
+    const double n = (double)a.G;
+    double c = 0.0, s1 = 0.0, s2 = 0.0;
+    if (on) {
+        c = a.hyper[((size_t)0 * a.P + p) * S + ch];
+        if (!finite64(c)) c = th[0];
+        for (int g = ty; g < a.G; g += NS) {
+            const double d = th[(size_t)g * S] - c;
+            s1 += d;
+            s2 = fma(d, d, s2);
+        }
+    }
+    red1[ty][tx] = s1;
+    red2[ty][tx] = s2;
+    __syncthreads();
+    if (ty == 0 && on) {
+        double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) { t1 += red1[k][tx]; t2 += red2[k][tx]; }
+        const double dmean = t1 / n;
+        const double muHat = c + dmean;                                           // numpy.mean, :485
+        const double sigma2_old = a.hyper[((size_t)1 * a.P + p) * S + ch];
+        const double sdm = sqrt(sigma2_old / n);                                  // :486
+        double z;
+        if (a.tape_zmu) z = a.tape_zmu[(size_t)p * S + ch];
+        else {
+            const uint4 r = philox_draw(a.chain_id0 + ch, a.seed, a.iter, MCMCN_STREAM_HYPER, (unsigned)p, 0u);
+            z = normal_from(r.x, r.y);
+        }
+        const double mu = __dadd_rn(muHat, __dmul_rn(sdm, z));                    // :487
+        const double dmu = mu - muHat;
+        const double ss = fma(n * dmu, dmu, fmax(fma(-dmean, t1, t2), 0.0));      // :494
+        const double hat = ss / (n - 1.0);
+        const double aa = (n - 1.0) / 2.0;
+        double q;                                                                 // unit inverse-gamma draw, :497-498
+        if (a.tape_qsig) q = a.tape_qsig[(size_t)p * S + ch];
+        else q = 1.0 / gamma_draw(aa, a.chain_id0 + ch, a.seed, a.iter, (unsigned)p);
+        const double sigma2 = __dadd_rn(__dmul_rn(q, __dmul_rn(aa, hat)), 0.0);
+        const double sd = sqrt(sigma2);
+        a.hyper[((size_t)0 * a.P + p) * S + ch] = mu;
+        a.hyper[((size_t)1 * a.P + p) * S + ch] = sigma2;
+        a.hyper[((size_t)2 * a.P + p) * S + ch] = sd;
+        a.hyper[((size_t)3 * a.P + p) * S + ch] = log(sd);
+        a.hyper[((size_t)4 * a.P + p) * S + ch] = 1.0 / sd;
+    }
+}
+
 // ---------------------------------------------------------------- retained-sample write-back
 // One row of StepMethod.values (:648-654, :780-787): per name [mu, sigma2 (partial)], theta[0..G-1].
 // store[(row*ncol + col)*S + chain]; a warp writes 32 consecutive chains.

@@ -290,7 +290,9 @@ int mcmcn_run(const mcmcn_model* m, const mcmcn_state* s, const mcmcn_run_args* 
             h.tape_qsig = r->tape_qsig ? r->tape_qsig + it * per_iter_h : nullptr;
             const dim3 hg((unsigned)((s->n_chains + 31) / 32), (unsigned)m->n_params, 1);
             tic(1);
-            if (m->n_groups >= 512) hyper_kernel<32><<<hg, dim3(32, 32, 1), 0, stream>>>(h);   // 24 us at C3 (8 slices: 27)
+            if (m->n_groups >= 512 && !getenv("MCMCN_HYPER_TWO_PASS"))
+                hyper_onepass_kernel<32><<<hg, dim3(32, 32, 1), 0, stream>>>(h);   // 21 us at C3 (two passes: 24)
+            else if (m->n_groups >= 512) hyper_kernel<32><<<hg, dim3(32, 32, 1), 0, stream>>>(h);
             else if (m->n_groups >= 64) hyper_kernel<8><<<hg, dim3(32, 8, 1), 0, stream>>>(h);
             else hyper_kernel<1><<<hg, dim3(32, 1, 1), 0, stream>>>(h);
             toc();

@@ -296,3 +296,29 @@ def test_convergence_from_device_store_matches_diagnostic():
     d = sd.Diagnostic(samples=draws, keys=keys)
     numpy.testing.assert_allclose(rhat.cpu().numpy(), [d.rhat[k] for k in keys], rtol=1e-10)
     numpy.testing.assert_allclose(ess.cpu().numpy(), [d.effectiveN[k] for k in keys], rtol=1e-10)
+
+
+def test_one_pass_hyper_update_equals_two_pass_at_c3_shape(monkeypatch):
+    """The Gibbs hyper update reads theta once when there are many groups (shifted sums); it must
+    agree with the two-pass kernel (the reference's formulas, :485-:495) on the same state and tape."""
+    import torch
+    from engine import Engine
+    obj, names, nResp, ranges = parity.syntheticRegression(G=1024, R=8, K=2)
+    out = {}
+    for label in ("one", "two"):
+        if label == "two":
+            monkeypatch.setenv("MCMCN_HYPER_TWO_PASS", "1")
+        eng = Engine(parity.deviceObjective(obj, nResp, "fp32"), 1024, nResp, "partial", 64, seed=3)
+        eng.initialise(names, ranges)
+        gen = torch.Generator(device="cpu").manual_seed(5)
+        P, G = 3, 1024
+        tape = {"z": torch.randn((1, P, G, eng.S), generator=gen, dtype=torch.float64).to(eng.device),
+                "u": torch.rand((1, P, G, eng.S), generator=gen, dtype=torch.float64).to(eng.device),
+                "zmu": torch.randn((1, P, eng.S), generator=gen, dtype=torch.float64).to(eng.device),
+                "qsig": torch.rand((1, P, eng.S), generator=gen, dtype=torch.float64).add_(0.5).to(eng.device)}
+        eng.run(0, 1, 0, 1, tape=tape)
+        torch.cuda.synchronize()
+        st = eng.getState()
+        out[label] = (st["mu"], st["sigma2"])
+    numpy.testing.assert_allclose(out["one"][0], out["two"][0], rtol=1e-13, atol=1e-13)
+    numpy.testing.assert_allclose(out["one"][1], out["two"][1], rtol=1e-12)
