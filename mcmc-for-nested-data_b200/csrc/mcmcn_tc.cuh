@@ -91,6 +91,14 @@ __device__ __forceinline__ unsigned tf32_rn(float v) { return (__float_as_uint(v
 #define MCMCN_TC_THREADS 128
 #define MCMCN_TC_ONES_BYTES 4096   /* [128][8] constant A operand of the ne MMA, in shared memory */
 
+// norm_logpdf_inv without its validity selects (about 20 instructions per sweep): sd = 0 (1/sd = inf,
+// log sd = -inf), sd = nan and x = nan come out as nan through the arithmetic itself, x = +-inf as
+// -inf, sd = inf as -inf -- what scipy's norm.logpdf returns (posteriorSampling.py:293-294, :500-502).
+__device__ __forceinline__ double tc_norm_logpdf(double x, double loc, double inv_scale, double log_scale) {
+    const double y = __dmul_rn(__dsub_rn(x, loc), inv_scale);
+    return __dsub_rn(__dsub_rn(-0.5 * __dmul_rn(y, y), MCMCN_LOG_SQRT_2PI), log_scale);
+}
+
 __device__ __forceinline__ void tmem_st1(unsigned addr, unsigned v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(addr), "r"(v) : "memory");
 }
@@ -282,7 +290,8 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
     tc_fence_after();
     const unsigned tbase = tmem_base_s;
     const unsigned tlane = tbase + ((unsigned)warp << 21);             // lane field = 32 * warp
-    const unsigned mb_tma0 = smem_u32(&mbar_s[0]), mb_mma = smem_u32(&mbar_s[2]);
+    unsigned mb_tma0 = smem_u32(&mbar_s[0]), mb_mma = smem_u32(&mbar_s[2]);
+    asm volatile("" : "+r"(mb_tma0), "+r"(mb_mma));                    // held in registers (else rebuilt from SR_CgaCtaId at every wait)
 
     const float* tc = reinterpret_cast<const float*>(a.tc_data);
     auto stage_group = [&](int s, int g) {                             // thread 0 only
@@ -357,8 +366,8 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
             const double prop = __dadd_rn(in.cur, __dmul_rn(in.sc, in.z));     // numpy.random.normal(value, sd), :304-306
             double lp_prop, lp_cur;
             if (partial) {
-                lp_prop = norm_logpdf_inv(prop, in.h_mu, in.h_isd, in.h_lsd);
-                lp_cur = (GENERAL && override_lp) ? in.lp_cur : norm_logpdf_inv(in.cur, in.h_mu, in.h_isd, in.h_lsd);
+                lp_prop = tc_norm_logpdf(prop, in.h_mu, in.h_isd, in.h_lsd);
+                lp_cur = (GENERAL && override_lp) ? in.lp_cur : tc_norm_logpdf(in.cur, in.h_mu, in.h_isd, in.h_lsd);
             } else {
                 lp_prop = prior_logpdf(a.prior[p], prop);
                 lp_cur = in.lp_cur;
