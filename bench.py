@@ -349,7 +349,7 @@ def runGpu(args):
     nKept = len(store.iterations)
     d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     diag = None
-    if nKept >= 4:
+    if nKept >= 6:                                   # two half-chains of at least 3 rows each (mcmcn_diag_ess)
         barrier()
         d0.record()
         rhat, ess = convergenceFromStore(store.tensor, nKept, chains, group=dist.group.WORLD if world > 1 else None)

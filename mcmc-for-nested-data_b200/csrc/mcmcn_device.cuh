@@ -407,35 +407,81 @@ struct Logit {
     template <int C, typename T>
     struct Work : PlainWork<P, C, T> {};
 
-    template <int C, typename T>
-    __device__ static __forceinline__ void accumulate(const T* __restrict__ blk, int nobs, const double*,
-                                                      const Work<C, T>& w, double (&acc)[C], const ObsCtx&) {
-        const int nq = nobs >> 2;
-        // FP32 partial sums over 16 observations, then folded into FP64 (the conversion runs on the
-        // same XU pipe as the two MUFU ops per evaluation that bound this objective)
-        for (int q0 = 0; q0 < nq; q0 += 4) {
-            T s[C];
+    // Whole quads, FP64 objective mode: the formula as written.
+    template <int C>
+    __device__ static __forceinline__ void quads(const double* __restrict__ blk, int nq, const Work<C, double>& w, double (&acc)[C]) {
+        for (int q = 0; q < nq; ++q) {
+            double x4[4], y4[4];
+            Vec4<double>::load(blk + (size_t)q * UNIT, x4);
+            Vec4<double>::load(blk + (size_t)q * UNIT + 4, y4);
 #pragma unroll
-            for (int c = 0; c < C; ++c) s[c] = (T)0;
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const double eta = fma(w.th[c][1], x4[j], w.th[c][0]);
+                    acc[c] += fma(y4[j], eta, -softplus_t(eta));
+                }
+            }
+        }
+    }
+    // Whole quads, FP32 (production) mode, 16 observations per FP64 fold.  Same function, arranged for
+    // the MUFU pipe that bounds it: with e = eta * log2(e) (the chain's a, b pre-scaled),
+    //     y*eta - softplus(eta) = ln2 * [ (y - 1/2) e - |e|/2 - log2(1 + 2^-|e|) ]
+    // and the sum of the 16 logarithms is the logarithm of the product of the 16 factors
+    // (1 + 2^-|e|), each in (1, 2]: one ex2 per observation, ONE lg2 per 16 observations (was one
+    // each), and four FFMA (e; product *= 1 + t; two for the linear part) instead of seven FP32 ops.
+    // The product of 16 factors carries 16 roundings of 6e-8 relative, i.e. the same absolute error
+    // in the logarithm as the sum of 16 rounded logarithms had.
+    template <int C>
+    __device__ static __forceinline__ void quads(const float* __restrict__ blk, int nq, const Work<C, float>& w, double (&acc)[C]) {
+        float a2[C], b2[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            a2[c] = w.th[c][0] * 1.4426950408889634f;
+            b2[c] = w.th[c][1] * 1.4426950408889634f;
+        }
+        for (int q0 = 0; q0 < nq; q0 += 4) {
+            float s[C], pr[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                s[c] = 0.0f;
+                pr[c] = 1.0f;
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 if (q0 + u < nq) {
-                    T x4[4], y4[4];
-                    Vec4<T>::load(blk + (size_t)(q0 + u) * UNIT, x4);
-                    Vec4<T>::load(blk + (size_t)(q0 + u) * UNIT + 4, y4);
+                    float x4[4], y4[4];
+                    Vec4<float>::load(blk + (size_t)(q0 + u) * UNIT, x4);
+                    Vec4<float>::load(blk + (size_t)(q0 + u) * UNIT + 4, y4);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
+                        const float yh = y4[j] - 0.5f;
 #pragma unroll
                         for (int c = 0; c < C; ++c) {
-                            const T eta = fma_t(w.th[c][1], x4[j], w.th[c][0]);
-                            s[c] += fma_t(y4[j], eta, -softplus_t(eta));
+                            const float e = fmaf(b2[c], x4[j], a2[c]);
+                            float t;
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(-fabsf(e)));
+                            pr[c] = fmaf(pr[c], t, pr[c]);
+                            s[c] = fmaf(yh, e, s[c]);
+                            s[c] = fmaf(-0.5f, fabsf(e), s[c]);
                         }
                     }
                 }
             }
 #pragma unroll
-            for (int c = 0; c < C; ++c) acc[c] += (double)s[c];
+            for (int c = 0; c < C; ++c) {
+                float l;
+                asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(pr[c]));
+                acc[c] += (double)(0.6931471805599453f * (s[c] - l));
+            }
         }
+    }
+
+    template <int C, typename T>
+    __device__ static __forceinline__ void accumulate(const T* __restrict__ blk, int nobs, const double*,
+                                                      const Work<C, T>& w, double (&acc)[C], const ObsCtx&) {
+        const int nq = nobs >> 2;
+        quads<C>(blk, nq, w, acc);
         const int rem = nobs & 3;
         const T* xq = blk + (size_t)nq * UNIT;
         for (int j = 0; j < rem; ++j) {
