@@ -90,6 +90,21 @@ __device__ __forceinline__ double normal_from(unsigned a, unsigned b) {
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));
     return (double)(r * __cosf(6.283185307179586f * u2));
 }
+// Both Box-Muller branches of the same two words: one Philox call serves two consecutive sweeps
+// of the step kernels (the cosine branch the even sweep, the sine branch the odd one).
+__device__ __forceinline__ void normal_pair_from(unsigned a, unsigned b, float& zc, float& zs) {
+    const float u1 = (float)((a >> 8) + 1u) * 5.9604644775390625e-8f;   // (0, 1]
+    const float u2 = (float)(b >> 8) * 5.9604644775390625e-8f;          // [0, 1)
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));
+    zc = r * __cosf(6.283185307179586f * u2);
+    zs = r * __sinf(6.283185307179586f * u2);
+}
+// (w + 0.5) * 2^-32 in (0, 1) from a 32-bit word without an integer-to-double conversion: the
+// word fills the top mantissa bits of a double in [1, 2), then one exact subtraction.
+__device__ __forceinline__ double uniform_from32(unsigned w) {
+    return __hiloint2double((int)(0x3FF00000u | (w >> 12)), (int)((w << 20) | 0x80000u)) - 1.0;
+}
 // log(u) < diff decided in FP32 when the margin allows: returns +1 (true), -1 (false) or 0
 // (too close to call: the caller falls back to the FP64 logarithm, about once per 10^5
 // decisions).  __logf is accurate to 2^-21.41 absolute on [0.5, 2] and 3 ulp elsewhere and
@@ -115,12 +130,13 @@ __device__ __forceinline__ double norm_logpdf(double x, double loc, double scale
     return (!(scale > 0.0) || y != y) ? __longlong_as_double(0x7ff8000000000000LL) : r;
 }
 // same with the reciprocal of the scale precomputed (group-level prior of partial pooling: two
-// evaluations per decision; differs from the quotient form by at most 1 ulp of y); branch-free
+// evaluations per decision; differs from the quotient form by at most 1 ulp of y).  No validity
+// selects: sd = 0 (1/sd = inf, log sd = -inf), sd = nan and x = nan come out as nan through the
+// arithmetic itself, x = +-inf and sd = inf as -inf -- what scipy's norm.logpdf returns
+// (posteriorSampling.py:293-294, :500-502).
 __device__ __forceinline__ double norm_logpdf_inv(double x, double loc, double inv_scale, double log_scale) {
     const double y = __dmul_rn(__dsub_rn(x, loc), inv_scale);
-    const double r = __dsub_rn(__dsub_rn(-0.5 * __dmul_rn(y, y), MCMCN_LOG_SQRT_2PI), log_scale);
-    const bool ok = inv_scale > 0.0 && inv_scale < __longlong_as_double(0x7ff0000000000000LL) && y == y;
-    return ok ? r : __longlong_as_double(0x7ff8000000000000LL);
+    return __dsub_rn(__dsub_rn(-0.5 * __dmul_rn(y, y), MCMCN_LOG_SQRT_2PI), log_scale);
 }
 __device__ __forceinline__ bool finite64(double v) {
     return (__double2hiint(v) & 0x7ff00000) != 0x7ff00000;
@@ -738,7 +754,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sweep_kernel(const SweepArgs a) {
     }
     // per-thread parking slots in shared memory behind the tile: [field][c][thread], 8 bytes each
     double* park = reinterpret_cast<double*>(smem_raw + a.tile_bytes);
-    enum { ST_PROP = 0, ST_U, ST_LPPROP, ST_LPCUR, ST_LLCUR, ST_OLD, ST_AUX };
+    enum { ST_PROP = 0, ST_U, ST_LPPROP, ST_LPCUR, ST_LLCUR, ST_OLD, ST_RAND2, ST_AUX };
 #define SLOT(f, c) park[((f) * C + (c)) * blockDim.x + threadIdx.x]
 
     for (int g = g0; g < g1; ++g) {
@@ -787,16 +803,29 @@ __global__ void __launch_bounds__(MAXT, MINB) sweep_kernel(const SweepArgs a) {
                         z[c] = a.tape_z[row + chl[c]];
                         uu[c] = a.tape_u[row + chl[c]];
                     }
-                } else {
+                } else if ((p & 1) == 0) {
+                    // One Philox4x32-10 call per two sweeps, the recipe of the tcgen05 step kernel (same
+                    // counters, same draws): words 0-1 -> two normals, words 2, 3 -> one uniform each;
+                    // the odd sweep's pair waits in a parking slot as (float z, 32-bit word).
                     uint4 rnd[C];
 #pragma unroll
                     for (int c = 0; c < C; ++c)
                         rnd[c] = philox_draw(a.chain_id0 + chl[c], a.seed, a.iter, MCMCN_STREAM_SWEEP,
-                                             (unsigned)(p * a.G + g), 0u);
+                                             (unsigned)((p >> 1) * a.G + g), 1u);
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
-                        z[c] = normal_from(rnd[c].x, rnd[c].y);
-                        uu[c] = uniform_from(rnd[c].z, rnd[c].w);
+                        float zc, zs;
+                        normal_pair_from(rnd[c].x, rnd[c].y, zc, zs);
+                        z[c] = (double)zc;
+                        uu[c] = uniform_from32(rnd[c].z);
+                        SLOT(ST_RAND2, c) = __hiloint2double((int)rnd[c].w, __float_as_int(zs));
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const double packed = SLOT(ST_RAND2, c);
+                        z[c] = (double)__int_as_float(__double2loint(packed));
+                        uu[c] = uniform_from32((unsigned)__double2hiint(packed));
                     }
                 }
 #pragma unroll

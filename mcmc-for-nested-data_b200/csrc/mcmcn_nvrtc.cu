@@ -164,7 +164,7 @@ int mcmcn_user_objective_compile(const char* source, int32_t n_params, int32_t o
     s.eval_one = (sweep_fn)(void*)k[7];
     s.pointwise = (pointwise_fn)(void*)k[8];
     s.elem_bytes = precision == 32 ? 4 : 8;
-    s.park_doubles = 6;
+    s.park_doubles = 7;
     *out_handle = uo;
     return MCMCN_OK;
 }

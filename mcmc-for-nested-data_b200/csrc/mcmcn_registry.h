@@ -19,7 +19,7 @@ struct KernelSet {
     sweep_fn eval_wide, eval_one;
     pointwise_fn pointwise;
     int elem_bytes;
-    int park_doubles;           // shared-memory parking slots per chain (6 + Aux doubles)
+    int park_doubles;           // shared-memory parking slots per chain (7 + Aux doubles)
 };
 
 #define MCMCN_SET(OBJ_ID, OBJ, KK, PREC, T, CW)                                                          \
@@ -27,7 +27,7 @@ struct KernelSet {
      {sweep_kernel<OBJ, CW, T, 3, 0, 128>, sweep_kernel<OBJ, CW, T, 3, 1, 128>,                          \
       sweep_kernel<OBJ, CW, T, 3, 2, 128>, sweep_kernel<OBJ, CW, T, 3, 3, 128>},                         \
      sweep_kernel<OBJ, CW, T, 2, -1>, sweep_kernel<OBJ, 1, T, 1, -1>,                                    \
-     eval_kernel<OBJ, CW, T>, eval_kernel<OBJ, 1, T>, pointwise_kernel<OBJ, T>, (int)sizeof(T), 6 + OBJ::AUX_DOUBLES}
+     eval_kernel<OBJ, CW, T>, eval_kernel<OBJ, 1, T>, pointwise_kernel<OBJ, T>, (int)sizeof(T), 7 + OBJ::AUX_DOUBLES}
 
 const KernelSet* sets_linreg_a(int* n);
 const KernelSet* sets_linreg_b(int* n);

@@ -91,14 +91,6 @@ __device__ __forceinline__ unsigned tf32_rn(float v) { return (__float_as_uint(v
 #define MCMCN_TC_THREADS 128
 #define MCMCN_TC_ONES_BYTES 4096   /* [128][8] constant A operand of the ne MMA, in shared memory */
 
-// norm_logpdf_inv without its validity selects (about 20 instructions per sweep): sd = 0 (1/sd = inf,
-// log sd = -inf), sd = nan and x = nan come out as nan through the arithmetic itself, x = +-inf as
-// -inf, sd = inf as -inf -- what scipy's norm.logpdf returns (posteriorSampling.py:293-294, :500-502).
-__device__ __forceinline__ double tc_norm_logpdf(double x, double loc, double inv_scale, double log_scale) {
-    const double y = __dmul_rn(__dsub_rn(x, loc), inv_scale);
-    return __dsub_rn(__dsub_rn(-0.5 * __dmul_rn(y, y), MCMCN_LOG_SQRT_2PI), log_scale);
-}
-
 __device__ __forceinline__ void tmem_st1(unsigned addr, unsigned v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(addr), "r"(v) : "memory");
 }
@@ -181,12 +173,6 @@ struct TcInputs {
 // (w + 0.5) * 2^-32 in (0, 1).  `stash` carries the second pair to the odd sweep.
 struct TcStash { double z, u; };
 
-// (w + 0.5) * 2^-32 in (0, 1) from a 32-bit word without an integer-to-double conversion: the
-// word fills the top mantissa bits of a double in [1, 2), then one exact subtraction.
-__device__ __forceinline__ double tc_uniform32(unsigned w) {
-    return __hiloint2double((int)(0x3FF00000u | (w >> 12)), (int)((w << 20) | 0x80000u)) - 1.0;
-}
-
 // `at` = element index of (name p, group g, this chain) in the [P][G][S] arrays, `hy` = p * S + chain
 // in the [5][P][S] hyper-parameters, `bb` = g * K + p in bbar; the caller bumps them per sweep.
 // State loads and random numbers are separate so that they can sit behind different MMAs.
@@ -216,14 +202,12 @@ __device__ __forceinline__ void tc_fetch_random(TcInputs& o, const SweepArgs& a,
         o.u = a.tape_u[at];
     } else if ((p & 1) == 0) {
         const uint4 rnd = philox_draw(a.chain_id0 + chl, a.seed, a.iter, MCMCN_STREAM_SWEEP, (unsigned)((p >> 1) * a.G + g), 1u);
-        const float u1 = (float)((rnd.x >> 8) + 1u) * 5.9604644775390625e-8f;   // (0, 1]
-        const float u2 = (float)(rnd.y >> 8) * 5.9604644775390625e-8f;          // [0, 1)
-        float r;
-        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));
-        o.z = (double)(r * __cosf(6.283185307179586f * u2));
-        stash.z = (double)(r * __sinf(6.283185307179586f * u2));
-        o.u = tc_uniform32(rnd.z);
-        stash.u = tc_uniform32(rnd.w);
+        float zc, zs;
+        normal_pair_from(rnd.x, rnd.y, zc, zs);
+        o.z = (double)zc;
+        stash.z = (double)zs;
+        o.u = uniform_from32(rnd.z);
+        stash.u = uniform_from32(rnd.w);
     } else {
         o.z = stash.z;
         o.u = stash.u;
@@ -366,8 +350,8 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
             const double prop = __dadd_rn(in.cur, __dmul_rn(in.sc, in.z));     // numpy.random.normal(value, sd), :304-306
             double lp_prop, lp_cur;
             if (partial) {
-                lp_prop = tc_norm_logpdf(prop, in.h_mu, in.h_isd, in.h_lsd);
-                lp_cur = (GENERAL && override_lp) ? in.lp_cur : tc_norm_logpdf(in.cur, in.h_mu, in.h_isd, in.h_lsd);
+                lp_prop = norm_logpdf_inv(prop, in.h_mu, in.h_isd, in.h_lsd);
+                lp_cur = (GENERAL && override_lp) ? in.lp_cur : norm_logpdf_inv(in.cur, in.h_mu, in.h_isd, in.h_lsd);
             } else {
                 lp_prop = prior_logpdf(a.prior[p], prop);
                 lp_cur = in.lp_cur;

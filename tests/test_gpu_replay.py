@@ -135,6 +135,25 @@ def test_tensor_core_and_fp32_pipe_kernels_agree_at_c3_size(monkeypatch):
     numpy.testing.assert_array_equal(out["tc"][1], out["pipe"][1])      # forced decisions: identical states
 
 
+def test_tensor_core_and_fp32_pipe_kernels_draw_the_same_random_numbers(monkeypatch):
+    """Free-running, same seed: both step kernels take their proposals and uniforms from the same
+    Philox counters (one call per two sweeps), so after a few iterations the two chains' states
+    are bit-identical except where a rounding-level difference of the log-likelihood flipped a
+    near-threshold decision."""
+    from engine import Engine
+    obj, names, nResp, ranges = parity.syntheticRegression(G=8, R=200, K=8)
+    out = {}
+    for label, env in (("tc", None), ("pipe", "1")):
+        if env:
+            monkeypatch.setenv("MCMCN_NO_TC", env)
+        eng = Engine(parity.deviceObjective(obj, nResp, "fp32"), 8, nResp, "partial", 160, seed=3)
+        eng.initialise(names, ranges)
+        eng.run(0, 3, 0, 1)
+        out[label] = eng.getState()
+    assert numpy.isfinite(out["tc"]["theta"]).all()
+    assert (out["tc"]["theta"] == out["pipe"]["theta"]).mean() > 0.995
+
+
 @pytest.mark.parametrize("pooling", ["partial", "none"])
 def test_replay_bernoulli_logit(pooling):
     obj, names, nResp, ranges = parity.syntheticLogit(G=30, R=50)
