@@ -201,14 +201,20 @@ def roofline(args, tensorCore, sweepMs, chains, peakFp32, peakTf32, peakMufu):
     observations rounded up to 16 -- and that pipe is the one that binds once latencies are hidden,
     so achieved = those TF32 flop over the launch time against the pipe's measured MMA rate."""
     G, R, K = args.groups, args.obs, args.coef
-    if K == 0:      # C5: 2 MUFU (ex2, lg2) + 6 FP32 flop per evaluation (SURVEY.md section 8d): the MUFU pipe binds
+    if K == 0:
+        # C5.  Algorithmic figure (SURVEY.md section 8d): 2 MUFU (ex2, lg2) + 6 FP32 flop per evaluation,
+        # the MUFU pipe binds -> `achieved` / `frac`.  The kernel itself executes one ex2 per evaluation
+        # and one lg2 per 16 (logarithm of the product of 16 factors), 1.0625 MUFU per evaluation:
+        # `mufu_pipe_utilisation` is that executed rate over the same peak.
         evals = 2.0 * G * R * chains
         ops = 2.0 * evals / (sweepMs * 1e-3)
+        executed = 1.0625 * evals / (sweepMs * 1e-3)
         return {"bound": "mufu", "kernel": "sweep_kernel<Logit,4,float>", "achieved": ops / 1e9, "peak": peakMufu / 1e9,
-                "unit": "Gop/s", "frac": ops / peakMufu, "mufu_per_eval": 2.0, "traffic": None,
+                "unit": "Gop/s", "frac": ops / peakMufu, "mufu_per_eval": 2.0, "mufu_executed_per_eval": 1.0625,
+                "mufu_pipe_utilisation": executed / peakMufu, "traffic": 2.499e9,
                 "fp32_pipe_peak_tflops": peakFp32 / 1e12,
                 "peak_source": "MUFU pipe limit measured in this run by an ex2-only microbenchmark (mcmcn_peak_mufu); "
-                               "nominal 148 SM x 16 lanes x 1.965 GHz = 4653"}
+                               "nominal 148 SM x 16 lanes x 1.965 GHz = 4653; traffic from profiles/r1_c5_kernel_ncu_summary.txt"}
     P, N = K + 1, G * R
     algFlops = FLOP_PER_EVAL * P * N * chains
     algTflops = algFlops / (sweepMs * 1e-3) / 1e12

@@ -449,20 +449,40 @@ struct Logit {
     // The product of 16 factors carries 16 roundings of 6e-8 relative, i.e. the same absolute error
     // in the logarithm as the sum of 16 rounded logarithms had.
     template <int C>
-    __device__ static __forceinline__ void quads(const float* __restrict__ blk, int nq, const Work<C, float>& w, double (&acc)[C]) {
-        float a2[C], b2[C];
+    __device__ static __forceinline__ void all_obs(const float* __restrict__ blk, int nobs, const Work<C, float>& w, double (&acc)[C]) {
+        const int nq = nobs >> 2, rem = nobs & 3;
+        float a2[C], b2[C], s[C], pr[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             a2[c] = w.th[c][0] * 1.4426950408889634f;
             b2[c] = w.th[c][1] * 1.4426950408889634f;
+            s[c] = 0.0f;
+            pr[c] = 1.0f;
         }
+#define MCMCN_LOGIT_OBS(xv, yv)                                                          \
+        {                                                                                \
+            const float yh = (yv) - 0.5f;                                                \
+            _Pragma("unroll") for (int c = 0; c < C; ++c) {                              \
+                const float e = fmaf(b2[c], (xv), a2[c]);                                \
+                float t;                                                                 \
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(-fabsf(e)));            \
+                pr[c] = fmaf(pr[c], t, pr[c]);                                           \
+                s[c] = fmaf(yh, e, s[c]);                                                \
+                s[c] = fmaf(-0.5f, fabsf(e), s[c]);                                      \
+            }                                                                            \
+        }
+#define MCMCN_LOGIT_FOLD()                                                               \
+        _Pragma("unroll") for (int c = 0; c < C; ++c) {                                  \
+            float l;                                                                     \
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(pr[c]));                    \
+            acc[c] += (double)(0.6931471805599453f * (s[c] - l));                        \
+            s[c] = 0.0f;                                                                 \
+            pr[c] = 1.0f;                                                                \
+        }
+        // the 1-3 observations of the last, partial quad join the first fold (at most 19 factors)
+        const float* xr = blk + (size_t)nq * UNIT;
+        for (int j = 0; j < rem; ++j) MCMCN_LOGIT_OBS(xr[j], xr[4 + j])
         for (int q0 = 0; q0 < nq; q0 += 4) {
-            float s[C], pr[C];
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                s[c] = 0.0f;
-                pr[c] = 1.0f;
-            }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 if (q0 + u < nq) {
@@ -470,25 +490,25 @@ struct Logit {
                     Vec4<float>::load(blk + (size_t)(q0 + u) * UNIT, x4);
                     Vec4<float>::load(blk + (size_t)(q0 + u) * UNIT + 4, y4);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float yh = y4[j] - 0.5f;
-#pragma unroll
-                        for (int c = 0; c < C; ++c) {
-                            const float e = fmaf(b2[c], x4[j], a2[c]);
-                            float t;
-                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(-fabsf(e)));
-                            pr[c] = fmaf(pr[c], t, pr[c]);
-                            s[c] = fmaf(yh, e, s[c]);
-                            s[c] = fmaf(-0.5f, fabsf(e), s[c]);
-                        }
-                    }
+                    for (int j = 0; j < 4; ++j) MCMCN_LOGIT_OBS(x4[j], y4[j])
                 }
             }
+            MCMCN_LOGIT_FOLD()
+        }
+        if (nq == 0) MCMCN_LOGIT_FOLD()
+#undef MCMCN_LOGIT_OBS
+#undef MCMCN_LOGIT_FOLD
+    }
+    template <int C>
+    __device__ static __forceinline__ void all_obs(const double* __restrict__ blk, int nobs, const Work<C, double>& w, double (&acc)[C]) {
+        const int nq = nobs >> 2, rem = nobs & 3;
+        quads<C>(blk, nq, w, acc);
+        const double* xq = blk + (size_t)nq * UNIT;
+        for (int j = 0; j < rem; ++j) {
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                float l;
-                asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(pr[c]));
-                acc[c] += (double)(0.6931471805599453f * (s[c] - l));
+                const double eta = fma(w.th[c][1], xq[j], w.th[c][0]);
+                acc[c] += fma(xq[4 + j], eta, -softplus_t(eta));
             }
         }
     }
@@ -496,17 +516,7 @@ struct Logit {
     template <int C, typename T>
     __device__ static __forceinline__ void accumulate(const T* __restrict__ blk, int nobs, const double*,
                                                       const Work<C, T>& w, double (&acc)[C], const ObsCtx&) {
-        const int nq = nobs >> 2;
-        quads<C>(blk, nq, w, acc);
-        const int rem = nobs & 3;
-        const T* xq = blk + (size_t)nq * UNIT;
-        for (int j = 0; j < rem; ++j) {
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const T eta = fma_t(w.th[c][1], xq[j], w.th[c][0]);
-                acc[c] += (double)fma_t(xq[4 + j], eta, -softplus_t(eta));
-            }
-        }
+        all_obs<C>(blk, nobs, w, acc);
     }
     struct Aux {};
     static constexpr int AUX_DOUBLES = 0;
