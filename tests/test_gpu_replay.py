@@ -135,6 +135,62 @@ def test_tensor_core_and_fp32_pipe_kernels_agree_at_c3_size(monkeypatch):
     numpy.testing.assert_array_equal(out["tc"][1], out["pipe"][1])      # forced decisions: identical states
 
 
+@pytest.mark.parametrize("workload", ["c3-tcgen05", "c3-fp32-pipe", "c5"])
+def test_full_size_iteration_matches_fp64_numpy(workload, monkeypatch):
+    """BASELINE configs 3 and 5 at their full data size (1,024 groups x 200 observations x 8
+    coefficients; 10,000 groups x 50 trials), 64 chains: one traced iteration with forced decisions.
+    Every proposal log-likelihood (P x G x chains of them) must be within 1e-5 relative of the
+    objective's formula (example/regression.py:53-67) evaluated in FP64 numpy on
+    the same proposals, and the state afterwards must be the forced one."""
+    import torch
+    from engine import Engine
+    nC = 64
+    if workload == "c5":
+        obj, names, nResp, ranges = parity.syntheticLogit(G=10000, R=50)
+        G, R, P = 10000, 50, 2
+        x, y = obj.x.reshape(G, R, 1), obj.y.reshape(G, R, 1)
+
+        def loglik(th):                                       # th [P][G][nC] -> [G][nC]
+            eta = th[0][:, None, :] + th[1][:, None, :] * x
+            return (y * eta - numpy.logaddexp(0.0, eta)).sum(axis=1)
+    else:
+        if workload == "c3-fp32-pipe":
+            monkeypatch.setenv("MCMCN_NO_TC", "1")
+        obj, names, nResp, ranges = parity.syntheticRegression(G=1024, R=200, K=8)
+        G, R, P = 1024, 200, 9
+        X, y = obj.X.reshape(G, R, 8), obj.y.reshape(G, R, 1)
+
+        def loglik(th):
+            resid = numpy.einsum("grk,kgn->grn", X, th[:8]) - y
+            sg = numpy.where(th[8] > 0, th[8], numpy.nan)     # scipy: scale <= 0 -> nan
+            return -0.5 * (resid ** 2).sum(axis=1) / sg ** 2 - R * (numpy.log(sg) + 0.5 * numpy.log(2 * numpy.pi))
+    eng = Engine(parity.deviceObjective(obj, nResp, "fp32"), G, nResp, "partial", nC, seed=5)
+    eng.initialise(names, ranges)
+    assert bool(eng.usesTensorCore) == (workload == "c3-tcgen05")
+    st0 = eng.getState()
+    gen = torch.Generator(device="cpu").manual_seed(13)
+    z = torch.randn((1, P, G, eng.S), generator=gen, dtype=torch.float64).mul_(0.05)
+    acc = (torch.rand((1, P, G, eng.S), generator=gen) < 0.4).to(torch.uint8)
+    tape = {"z": z.to(eng.device), "u": torch.rand((1, P, G, eng.S), generator=gen, dtype=torch.float64).to(eng.device),
+            "accept": acc.to(eng.device),
+            "zmu": torch.randn((1, P, eng.S), generator=gen, dtype=torch.float64).to(eng.device),
+            "qsig": torch.rand((1, P, eng.S), generator=gen, dtype=torch.float64).add_(0.5).to(eng.device)}
+    tr = eng.run(0, 1, 0, 1, tape=tape, trace=True)
+    torch.cuda.synchronize()
+    got = tr["ll"][0, ..., :nC].cpu().numpy()
+    theta = st0["theta"].copy()
+    zz, aa = z[0, ..., :nC].numpy(), acc[0, ..., :nC].numpy() != 0
+    worst = 0.0
+    for p in range(P):
+        prop = theta[p] + st0["scale"][p] * zz[p]
+        cand = theta.copy()
+        cand[p] = prop
+        worst = max(worst, parity.relErr(got[p], loglik(cand)).max())
+        theta[p] = numpy.where(aa[p], prop, theta[p])
+    assert worst <= 1e-5, worst
+    numpy.testing.assert_array_equal(eng.getState()["theta"], theta)
+
+
 def test_tensor_core_and_fp32_pipe_kernels_draw_the_same_random_numbers(monkeypatch):
     """Free-running, same seed: both step kernels take their proposals and uniforms from the same
     Philox counters (one call per two sweeps), so after a few iterations the two chains' states
