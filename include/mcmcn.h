@@ -65,15 +65,26 @@ extern "C" {
 #define MCMCN_PRIOR_UNIFORM 2
 #define MCMCN_PRIOR_EXPON 3
 #define MCMCN_PRIOR_HALFNORM 4
+#define MCMCN_PRIOR_LOGNORM 5     /* a = s */
+#define MCMCN_PRIOR_CAUCHY 6
+#define MCMCN_PRIOR_T 7           /* a = df */
+#define MCMCN_PRIOR_BETA 8        /* a, b */
+#define MCMCN_PRIOR_INVGAMMA 9    /* a */
+#define MCMCN_PRIOR_LAPLACE 10
+#define MCMCN_PRIOR_LOGISTIC 11
+#define MCMCN_PRIOR_CHI2 12       /* a = df */
 
 typedef struct mcmcn_prior {
     int32_t family;
     int32_t reserved;
-    double a;            /* shape (gamma) */
+    double a;            /* first shape parameter (gamma a, lognorm s, t / chi2 df, beta a, invgamma a) */
     double loc;
     double scale;
     double log_scale;    /* log(scale), precomputed by the host in fp64 */
-    double c0;           /* family constant: gammaln(a) for gamma */
+    double c0;           /* family constant, precomputed by the host in fp64: gammaln(a) (gamma, invgamma),
+                            2 s^2 (lognorm), log(poch(df/2, 1/2)) - (log(df) + log(pi))/2 (t), betaln(a, b) (beta),
+                            gammaln(df/2) (chi2) */
+    double b;            /* second shape parameter (beta b); chi2: log(2) df / 2 */
 } mcmcn_prior;
 
 /* The model: objective + observation data + group structure + priors.

@@ -171,6 +171,52 @@ __device__ __forceinline__ double prior_logpdf(const mcmcn_prior& pr, double x) 
             if (y < 0.0) return ninf;
             r = __dsub_rn(-0.22579135264472741, 0.5 * __dmul_rn(y, y));
             break;
+        case MCMCN_PRIOR_LOGNORM: {  // -log(y)**2 / (2 s**2) - log(s*y*sqrt(2 pi)); y == 0 -> -inf
+            if (y <= 0.0) return ninf;
+            const double ly = log(y);
+            r = __dsub_rn(__ddiv_rn(-__dmul_rn(ly, ly), pr.c0), log(__dmul_rn(__dmul_rn(pr.a, y), 2.5066282746310002)));
+            break;
+        }
+        case MCMCN_PRIOR_CAUCHY: {  // |y| < 1: -log(pi) - log1p(y**2); else -log(pi) - (2 log|y| + log1p((1/|y|)**2))
+            const double ay = fabs(y);
+            if (ay < 1.0) {
+                r = __dsub_rn(-1.1447298858494002, log1p(__dmul_rn(ay, ay)));
+            } else {
+                const double iy = __ddiv_rn(1.0, ay);
+                r = __dsub_rn(-1.1447298858494002, __dadd_rn(__dmul_rn(2.0, log(ay)), log1p(__dmul_rn(iy, iy))));
+            }
+            break;
+        }
+        case MCMCN_PRIOR_T:  // c0 - (df + 1)/2 * log1p(y*y/df)
+            r = __dsub_rn(pr.c0, __dmul_rn(__ddiv_rn(__dadd_rn(pr.a, 1.0), 2.0), log1p(__ddiv_rn(__dmul_rn(y, y), pr.a))));
+            break;
+        case MCMCN_PRIOR_BETA: {  // xlog1py(b-1, -y) + xlogy(a-1, y) - betaln(a, b)
+            if (y < 0.0 || y > 1.0) return ninf;
+            const double bm1 = __dsub_rn(pr.b, 1.0), am1 = __dsub_rn(pr.a, 1.0);
+            const double t1 = (bm1 == 0.0) ? 0.0 : __dmul_rn(bm1, log1p(-y));
+            const double t2 = (am1 == 0.0) ? 0.0 : __dmul_rn(am1, log(y));
+            r = __dsub_rn(__dadd_rn(t1, t2), pr.c0);
+            break;
+        }
+        case MCMCN_PRIOR_INVGAMMA:  // -(a+1) log(y) - gammaln(a) - 1/y
+            if (y < 0.0) return ninf;
+            r = __dsub_rn(__dsub_rn(__dmul_rn(-__dadd_rn(pr.a, 1.0), log(y)), pr.c0), __ddiv_rn(1.0, y));
+            break;
+        case MCMCN_PRIOR_LAPLACE:  // log(0.5 * exp(-|y|)) (scipy has no _logpdf: log of the pdf)
+            r = log(__dmul_rn(0.5, exp(-fabs(y))));
+            break;
+        case MCMCN_PRIOR_LOGISTIC: {  // t = -|y|; t - 2 log1p(exp(t))
+            const double t = -fabs(y);
+            r = __dsub_rn(t, __dmul_rn(2.0, log1p(exp(t))));
+            break;
+        }
+        case MCMCN_PRIOR_CHI2: {  // xlogy(df/2 - 1, y) - y/2 - gammaln(df/2) - log(2) df / 2
+            if (y < 0.0) return ninf;
+            const double hm1 = __dsub_rn(__ddiv_rn(pr.a, 2.0), 1.0);
+            const double xl = (hm1 == 0.0) ? 0.0 : __dmul_rn(hm1, log(y));
+            r = __dsub_rn(__dsub_rn(__dsub_rn(xl, __ddiv_rn(y, 2.0)), pr.c0), pr.b);
+            break;
+        }
         default:
             return nan_;
     }

@@ -58,7 +58,9 @@ def priorFromScipy(frozen):
     pr.loc, pr.scale = float(loc), float(scale)
     with numpy.errstate(all="ignore"):
         pr.log_scale = float(numpy.log(float(scale)))
-    pr.a, pr.c0 = 0.0, 0.0
+    pr.a, pr.c0, pr.b = 0.0, 0.0, 0.0
+    # every constant below is formed exactly as scipy's _logpdf forms it, so that the device value
+    # differs from frozen.logpdf only by the rounding of log / log1p / exp
     if name == "norm":
         pr.family = nat.PRIOR_NORM
     elif name == "gamma":
@@ -71,9 +73,40 @@ def priorFromScipy(frozen):
         pr.family = nat.PRIOR_EXPON
     elif name == "halfnorm":
         pr.family = nat.PRIOR_HALFNORM
+    elif name == "lognorm":
+        pr.family = nat.PRIOR_LOGNORM
+        pr.a = float(shapes[0])
+        pr.c0 = float(2 * pr.a ** 2)
+    elif name == "cauchy":
+        pr.family = nat.PRIOR_CAUCHY
+    elif name == "t":
+        pr.family = nat.PRIOR_T
+        pr.a = float(shapes[0])
+        if not numpy.isfinite(pr.a):
+            raise ValueError("t prior with df = inf: use norm")
+        pr.c0 = float(numpy.log(scipy.special.poch(0.5 * pr.a, 0.5)) - 0.5 * (numpy.log(pr.a) + numpy.log(numpy.pi)))
+    elif name == "beta":
+        pr.family = nat.PRIOR_BETA
+        pr.a, pr.b = float(shapes[0]), float(shapes[1])
+        pr.c0 = float(scipy.special.betaln(pr.a, pr.b))
+    elif name == "invgamma":
+        pr.family = nat.PRIOR_INVGAMMA
+        pr.a = float(shapes[0])
+        pr.c0 = float(scipy.special.gammaln(pr.a))
+    elif name == "laplace":
+        pr.family = nat.PRIOR_LAPLACE
+    elif name == "logistic":
+        pr.family = nat.PRIOR_LOGISTIC
+    elif name == "chi2":
+        pr.family = nat.PRIOR_CHI2
+        pr.a = float(shapes[0])
+        pr.c0 = float(scipy.special.gammaln(pr.a / 2.))
+        pr.b = float((numpy.log(2) * pr.a) / 2.)
     else:
-        raise ValueError("prior family %r has no device implementation "
-                         "(supported: norm, gamma, uniform, expon, halfnorm)" % name)
+        raise ValueError("prior family %r has no device implementation (supported: norm, gamma, uniform, expon, "
+                         "halfnorm, lognorm, cauchy, t, beta, invgamma, laplace, logistic, chi2)" % name)
+    if not frozen.dist._argcheck(*shapes) or not (float(scale) > 0):
+        raise ValueError("invalid parameters for prior %r" % name)
     return pr
 
 

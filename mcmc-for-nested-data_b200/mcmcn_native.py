@@ -29,6 +29,14 @@ PRIOR_GAMMA = 1
 PRIOR_UNIFORM = 2
 PRIOR_EXPON = 3
 PRIOR_HALFNORM = 4
+PRIOR_LOGNORM = 5
+PRIOR_CAUCHY = 6
+PRIOR_T = 7
+PRIOR_BETA = 8
+PRIOR_INVGAMMA = 9
+PRIOR_LAPLACE = 10
+PRIOR_LOGISTIC = 11
+PRIOR_CHI2 = 12
 
 ERRORS = {-1: "invalid argument", -2: "CUDA error", -3: "unsupported", -4: "NVRTC error"}
 
@@ -38,7 +46,7 @@ c_void_p = ctypes.c_void_p
 class Prior(ctypes.Structure):
     _fields_ = [("family", ctypes.c_int32), ("reserved", ctypes.c_int32),
                 ("a", ctypes.c_double), ("loc", ctypes.c_double), ("scale", ctypes.c_double),
-                ("log_scale", ctypes.c_double), ("c0", ctypes.c_double)]
+                ("log_scale", ctypes.c_double), ("c0", ctypes.c_double), ("b", ctypes.c_double)]
 
 
 class Model(ctypes.Structure):

@@ -236,9 +236,17 @@ def test_replay_streaming_group_larger_than_tile():
     parity.checkReplay(res, 1e-11, 0.0)
 
 
-def test_ragged_groups_and_prior_families():
+@pytest.mark.parametrize("families", ["uniform-expon-halfnorm", "cauchy-t-lognorm", "laplace-logistic-invgamma",
+                                      "beta-norm-chi2"])
+def test_ragged_groups_and_prior_families(families):
+    """Every device prior family against frozen scipy distributions (what the reference takes in
+    priorDistribution, posteriorSampling.py:293-294): proposal log-prior within 1e-12, FP64
+    trajectory identical."""
     obj, names, nResp, ranges = parity.syntheticRegression(G=9, R=7, K=2, ragged=True)
-    prior = [scipy.stats.uniform(-20, 40), scipy.stats.expon(-6, 4), scipy.stats.halfnorm(0, 3)]
+    prior = {"uniform-expon-halfnorm": [scipy.stats.uniform(-20, 40), scipy.stats.expon(-6, 4), scipy.stats.halfnorm(0, 3)],
+             "cauchy-t-lognorm": [scipy.stats.cauchy(0, 5), scipy.stats.t(4, 1, 3), scipy.stats.lognorm(0.8, scale=2)],
+             "laplace-logistic-invgamma": [scipy.stats.laplace(0, 4), scipy.stats.logistic(1, 3), scipy.stats.invgamma(3, scale=2)],
+             "beta-norm-chi2": [scipy.stats.beta(2, 3, loc=-30, scale=60), scipy.stats.norm(0, 10), scipy.stats.chi2(4)]}[families]
     res = parity.replay(obj, names, 9, nResp, "none", prior, ranges, nChains=3, nIter=150,
                         nSamples=50, precision="fp64", force=False)
     err, ties = parity.checkReplay(res, 1e-11, 0.0)

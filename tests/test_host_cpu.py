@@ -159,8 +159,19 @@ def test_prior_mapping():
     pr = priorFromScipy(scipy.stats.norm(loc=100, scale=10))
     assert (pr.family, pr.loc, pr.scale, pr.log_scale) == (nat.PRIOR_NORM, 100.0, 10.0, float(numpy.log(10.0)))
     assert priorFromScipy(scipy.stats.uniform(-2, 4)).family == nat.PRIOR_UNIFORM
+    pr = priorFromScipy(scipy.stats.t(4, 1, 3))
+    assert (pr.family, pr.a, pr.loc, pr.scale) == (nat.PRIOR_T, 4.0, 1.0, 3.0)
+    assert pr.c0 == float(numpy.log(scipy.special.poch(2.0, 0.5)) - 0.5 * (numpy.log(4.0) + numpy.log(numpy.pi)))
+    pr = priorFromScipy(scipy.stats.beta(2, 3, loc=-30, scale=60))
+    assert (pr.family, pr.a, pr.b, pr.c0) == (nat.PRIOR_BETA, 2.0, 3.0, float(scipy.special.betaln(2.0, 3.0)))
+    for frozen, fam in ((scipy.stats.lognorm(0.8, scale=2), nat.PRIOR_LOGNORM), (scipy.stats.cauchy(0, 5), nat.PRIOR_CAUCHY),
+                        (scipy.stats.invgamma(3), nat.PRIOR_INVGAMMA), (scipy.stats.laplace(), nat.PRIOR_LAPLACE),
+                        (scipy.stats.logistic(1, 3), nat.PRIOR_LOGISTIC), (scipy.stats.chi2(4), nat.PRIOR_CHI2)):
+        assert priorFromScipy(frozen).family == fam
     with pytest.raises(ValueError):
-        priorFromScipy(scipy.stats.cauchy())
+        priorFromScipy(scipy.stats.weibull_min(2))
+    with pytest.raises(ValueError):
+        priorFromScipy(scipy.stats.gamma(-1))
 
 
 class _FakeEngine(object):
