@@ -64,6 +64,17 @@ def makeLogitWorkload(G, R, seed=20261019):
     return x, y, ("a", "b"), {"a": [-2, 2], "b": [-1, 3]}
 
 
+def fixedPriors(args):
+    """Priors of the no-pooling variant (C5 uses N(0, 5) x 2; the regression
+    shape N(0, 10) on the coefficients and Gamma(2) on sigma); None for partial pooling."""
+    if args.pooling == "partial":
+        return None
+    import scipy.stats
+    if args.coef == 0:
+        return [scipy.stats.norm(0, 5), scipy.stats.norm(0, 5)]
+    return [scipy.stats.norm(0, 10)] * args.coef + [scipy.stats.gamma(2)]
+
+
 def schedule(args):
     """A (warmup+steps)-step slice of C3's schedule: burn = half the iterations, thin 10."""
     total = (args.warmup + args.steps) * args.iters_per_step
@@ -122,7 +133,7 @@ class ClockSampler(object):
 def _cpuChainWorker(job):
     """One chain of the oracle port for `nIter` iterations at the bench shape; returns seconds
     spent in the iteration loop (start-up excluded, like the GPU arm)."""
-    chain, nIter, G, R, K = job
+    chain, nIter, G, R, K, pooling, prior = job
     from oracle import posterior_oracle as po
     if K == 0:                                   # C5: Bernoulli-logit
         x, y, names, ranges = makeLogitWorkload(G, R)
@@ -130,8 +141,8 @@ def _cpuChainWorker(job):
     else:
         X, y, names, ranges = makeWorkload(G, R, K)
         obj = po.LinearRegressionObjective(X, y)
-    oc = po.OracleChain(chain, chain, max(nIter, 10), max(nIter, 10) // 2, names, G, R, "partial",
-                        obj, None, False, ranges)
+    oc = po.OracleChain(chain, chain, max(nIter, 10), max(nIter, 10) // 2, names, G, R, pooling,
+                        obj, prior, False, ranges)
     oc.nIter = nIter
     t0 = time.perf_counter()
     oc.run(keepRows=False)
@@ -142,7 +153,7 @@ def cpuBaseline(args, cores, iters):
     """chain-iterations/s of the oracle port (the reference's algorithm restated in numpy) on
     `cores` host processes, `iters` iterations of one chain each."""
     import multiprocessing
-    jobs = [(c, iters, args.groups, args.obs, args.coef) for c in range(cores)]
+    jobs = [(c, iters, args.groups, args.obs, args.coef, args.pooling, fixedPriors(args)) for c in range(cores)]
     t0 = time.perf_counter()
     if cores == 1:
         dt = _cpuChainWorker(jobs[0])
@@ -182,9 +193,10 @@ def runReference(args):
 
 
 def workloadConfig(args, chains):
-    name = ("C3: hierarchical linear regression, partial pooling, %d groups x %d obs x %d coefficients (+sigma)"
-            % (args.groups, args.obs, args.coef)) if args.coef else \
-           ("C5: hierarchical Bernoulli-logit, partial pooling, %d groups x %d trials, 2 parameters" % (args.groups, args.obs))
+    pool = {"partial": "partial pooling", "none": "no pooling (fixed priors)"}[args.pooling]
+    name = ("C3: hierarchical linear regression, %s, %d groups x %d obs x %d coefficients (+sigma)"
+            % (pool, args.groups, args.obs, args.coef)) if args.coef else \
+           ("C5: hierarchical Bernoulli-logit, %s, %d groups x %d trials, 2 parameters" % (pool, args.groups, args.obs))
     return {"workload": name,
             "chains_per_gpu": chains, "iters_per_step": args.iters_per_step,
             "schedule": "burn = first half of the run (tune every 100), thin %d after" % args.thin,
@@ -269,7 +281,7 @@ def runGpu(args):
         X, y, names, ranges = makeWorkload(G, R, K)
         obj = Objective.linear_regression(X, y, args.precision)
     P = len(names)
-    eng = Engine(obj, G, R, "partial", chains, chainId0=rank * chains, seed=args.seed)
+    eng = Engine(obj, G, R, args.pooling, chains, priorDistribution=fixedPriors(args), chainId0=rank * chains, seed=args.seed)
     eng.initialise(names, ranges)
     total, burn, thin = schedule(args)
     ips = args.iters_per_step
@@ -315,7 +327,8 @@ def runGpu(args):
     rowBytes = eng.nCol * eng.S * 4
     maxRows = ips // thin + 1
     pinRows = torch.empty((maxRows, eng.nCol, eng.S), dtype=torch.float32).pin_memory()
-    pinHyper = torch.empty((5, P, eng.S), dtype=torch.float64).pin_memory()
+    hyper = eng.hyper if eng.hyper is not None else torch.zeros((1, 1, eng.S), dtype=torch.float64, device=dev)
+    pinHyper = torch.empty(tuple(hyper.shape), dtype=torch.float64).pin_memory()
     eng.seed = args.seed + 1
     store.iterations = store.iterations[:len([i for i in range(args.warmup * ips) if i % thin == 0 and i >= burn])]
     h2d = pinData.numel() * pinData.element_size()
@@ -325,7 +338,7 @@ def runGpu(args):
     # computes; every copy is finished before the closing event (the main stream waits for the copy stream)
     main = torch.cuda.current_stream(dev)
     side = torch.cuda.Stream(dev)
-    hyperSnap = torch.empty_like(eng.hyper)          # the step's hyper-parameters, frozen before the next step overwrites them
+    hyperSnap = torch.empty_like(hyper)          # the step's hyper-parameters, frozen before the next step overwrites them
     snapFree = torch.cuda.Event()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -336,7 +349,7 @@ def runGpu(args):
         r1 = len(store.iterations)
         if k:
             main.wait_event(snapFree)
-        hyperSnap.copy_(eng.hyper, non_blocking=True)
+        hyperSnap.copy_(hyper, non_blocking=True)
         side.wait_stream(main)
         with torch.cuda.stream(side):
             if r1 > r0:                              # retained rows are append-only: nothing overwrites them
@@ -428,6 +441,8 @@ def main():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--cpu-iters", type=int, default=40)
     ap.add_argument("--ref-iters", type=int, default=5)
+    ap.add_argument("--pooling", default="partial", choices=["partial", "none"],
+                    help="partial (default, the BASELINE metric's mode) or none (BASELINE config 5 names both)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--traffic", type=float, default=208.0e6,
                     help="dram__bytes_read.sum + dram__bytes_write.sum per step-kernel launch, from the committed "

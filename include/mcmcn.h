@@ -128,6 +128,14 @@ typedef struct mcmcn_model {
     const int64_t* tc_group_off;     /* device [G+1], in floats */
     int64_t tc_max_block_floats;     /* largest block */
     mcmcn_prior prior[MCMCN_MAX_PARAMS];   /* none / complete pooling only */
+    /* Complete pooling at scale (optional, NULL = step the single group of all N observations with
+     * one warp per 128 chains).  `split` describes the SAME observations as many small groups (its
+     * pooling field is ignored); each sweep then evaluates the proposal's log-likelihood over those
+     * groups in parallel (observations x chains across the whole GPU), sums the partial sums in group
+     * order per chain and takes the decision in a per-chain kernel (CompletePooling,
+     * posteriorSampling.py:662-685).  `split_scratch`: device, (P + split->n_groups + 3) * stride doubles. */
+    const struct mcmcn_model* split;
+    double* split_scratch;
 } mcmcn_model;
 
 /* Chain state of the n_chains chains resident on this device

@@ -1254,6 +1254,113 @@ __global__ void __launch_bounds__(32 * NS) hyper_onepass_kernel(const HyperArgs 
 // ---------------------------------------------------------------- retained-sample write-back
 // One row of StepMethod.values (:648-654, :780-787): per name [mu, sigma2 (partial)], theta[0..G-1].
 // store[(row*ncol + col)*S + chain]; a warp writes 32 consecutive chains.
+// ---------------------------------------------------------------- complete pooling, split over observations
+// One group of all N observations (CompletePooling, posteriorSampling.py:662-685) leaves only the
+// chains to parallelise over in the step kernel.  When the host provides the same observations as
+// many small groups (mcmcn_model.split), a sweep of name p is three launches: propose (per chain),
+// eval_kernel over the small groups with the candidate vector as pooled parameters (observations x
+// chains across the GPU), decide (per chain: partial sums added in group order, then the same
+// decision tree, tuning and random-number recipe as the step kernels).
+struct CompleteArgs {
+    int P, p, n_chains, S, n_parts;
+    long long chain_id0, iter;
+    unsigned long long seed;
+    int tune, count;
+    mcmcn_prior prior;            // of name p
+    double* theta;                // [P][1][S]
+    double* scale;
+    unsigned* counts;
+    double* ll;                   // [1][S]
+    double* lprior;               // [P][1][S]
+    double* cand;                 // [P][S] candidate vector: current values, name p replaced by the proposal
+    double* part;                 // [n_parts][S] log-likelihood of the candidate per small group
+    double* park;                 // [3][S] proposal, uniform, proposal log-prior
+    const double* tape_z;         // [P][1][S] of this iteration, or null
+    const double* tape_u;
+    const unsigned char* tape_acc;
+    double* tr_ll;
+    double* tr_lp;
+    double* tr_diff;
+    unsigned char* tr_acc;
+};
+
+static __global__ void __launch_bounds__(128) complete_propose_kernel(const CompleteArgs a) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.S) return;
+    const int chl = min(c, a.n_chains - 1);
+    const size_t S = (size_t)a.S, at = (size_t)a.p * S + chl;
+    double z, u;
+    if (a.tape_z) {
+        z = a.tape_z[at];
+        u = a.tape_u[at];
+    } else {                      // the step kernels' recipe with G = 1: one Philox call per two sweeps
+        const uint4 rnd = philox_draw(a.chain_id0 + chl, a.seed, a.iter, MCMCN_STREAM_SWEEP, (unsigned)(a.p >> 1), 1u);
+        float zc, zs;
+        normal_pair_from(rnd.x, rnd.y, zc, zs);
+        z = (double)((a.p & 1) ? zs : zc);
+        u = uniform_from32((a.p & 1) ? rnd.w : rnd.z);
+    }
+    const double prop = __dadd_rn(a.theta[at], __dmul_rn(a.scale[at], z));   // :304-306
+    for (int k = 0; k < a.P; ++k) a.cand[(size_t)k * S + c] = (k == a.p) ? prop : a.theta[(size_t)k * S + chl];
+    a.park[c] = prop;
+    a.park[S + c] = u;
+    a.park[2 * S + c] = prior_logpdf(a.prior, prop);
+}
+
+static __global__ void __launch_bounds__(128) complete_decide_kernel(const CompleteArgs a) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_chains) return;
+    const size_t S = (size_t)a.S, at = (size_t)a.p * S + c;
+    double llp = 0.0;                                                   // fixed order: group 0, 1, 2, ...
+#pragma unroll 8
+    for (int g = 0; g < a.n_parts; ++g) llp += a.part[(size_t)g * S + c];
+    const double prop = a.park[c], u = a.park[S + c], lp_prop = a.park[2 * S + c];
+    // Parameter.step decision tree, :334-367
+    const double post_prop = lp_prop + llp;
+    const double post_cur = a.lprior[at] + a.ll[c];
+    const double diff = post_prop - post_cur;
+    const bool b1 = !finite64(post_cur) && finite64(post_prop);
+    const bool test = finite64(llp) && finite64(diff);                 // branches 4/5 draw the uniform
+    const int fast = log_u_vs_diff_fast(u, diff);
+    bool accept = b1 || (test && fast > 0);
+    if (!b1 && test && fast == 0) accept = log(u) < diff;
+    if (a.tr_ll) {
+        a.tr_ll[at] = llp;
+        a.tr_lp[at] = lp_prop;
+        a.tr_diff[at] = diff;
+        a.tr_acc[at] = accept ? 1 : 0;
+    }
+    if (a.tape_acc) accept = a.tape_acc[at] != 0;
+    if (accept) {                                                       // :369-378
+        a.theta[at] = prop;
+        a.lprior[at] = lp_prop;
+        a.ll[c] = llp;
+    }
+    if (a.count) {
+        unsigned cnt = a.counts[at];
+        cnt += accept ? 1u : 0x10000u;
+        if (a.tune) {                                                   // Parameter.tune, :385-437
+            const unsigned na = cnt & 0xFFFFu, nr = cnt >> 16;
+            if (na + nr) {
+                const double sc = a.scale[at];
+                const double rate = (double)na / (double)(na + nr);
+                double f = 1.0;
+                if (rate < 0.001) f = 0.1;
+                else if (rate < 0.05) f = 0.5;
+                else if (rate < 0.2) f = 0.9;
+                else if (rate > 0.95) f = 10.0;
+                else if (rate > 0.75) f = 2.0;
+                else if (rate > 0.5) f = 1.1;
+                double ns = __dmul_rn(sc, f);
+                if (ns == 0.0) ns = sc;
+                a.scale[at] = ns;
+                cnt = 0;
+            }
+        }
+        a.counts[at] = cnt;
+    }
+}
+
 template <typename TS>
 __global__ void snapshot_kernel(int P, int G, int partial, int n_chains, int S, const double* theta,
                                 const double* hyper, TS* store_row) {

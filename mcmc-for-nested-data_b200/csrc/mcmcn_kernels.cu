@@ -181,6 +181,79 @@ static int set_smem_attr(const void* fn, size_t smem) {
     return MCMCN_OK;
 }
 
+// Complete pooling with the observations split into small groups (mcmcn_model.split): per sweep
+// propose -> eval over the small groups -> decide.  Same iteration bookkeeping as mcmcn_run.
+static int run_complete_split(const mcmcn_model* m, const mcmcn_state* s, const mcmcn_run_args* r, cudaStream_t stream) {
+    const mcmcn_model* e = m->split;
+    const KernelSet* ks = nullptr;
+    int rc = validate(e, s, &ks);
+    if (rc) return rc;
+    if (e->n_params != m->n_params || e->n_obs != m->n_obs || e->objective != m->objective || e->precision != m->precision) {
+        set_error("split model does not describe the same objective / observations");
+        return MCMCN_ERR_INVALID;
+    }
+    if (!m->split_scratch) { set_error("split_scratch missing"); return MCMCN_ERR_INVALID; }
+    const int P = m->n_params, S = s->stride;
+    SweepArgs ea;
+    fill_args(ea, ks, e, s);
+    double* cand = m->split_scratch;
+    double* part = cand + (size_t)P * S;
+    double* park = part + (size_t)e->n_groups * S;
+    ea.pooled_theta = cand;
+    ea.out_ll = part;
+    const Geometry g = geometry(ks, e, s->n_chains);
+    ea.tile_bytes = (int)g.tile_bytes;
+    const sweep_fn efn = g.wide ? ks->eval_wide : ks->eval_one;
+    rc = set_smem_attr((const void*)efn, g.tile_bytes);
+    if (rc) return rc;
+
+    CompleteArgs c;
+    memset(&c, 0, sizeof(c));
+    c.P = P; c.n_chains = s->n_chains; c.S = S; c.n_parts = e->n_groups;
+    c.chain_id0 = s->chain_id0; c.seed = r->seed;
+    c.theta = s->theta; c.scale = s->scale; c.counts = s->counts; c.ll = s->ll; c.lprior = s->lprior;
+    c.cand = cand; c.part = part; c.park = park;
+    const size_t per_iter = (size_t)P * S;
+    long long last_tune = 0;
+    if (r->burn > 0) last_tune = ((long long)(r->burn - 1) / r->tune_interval) * r->tune_interval;
+    int64_t row = r->store_row0;
+    const unsigned nb = (unsigned)((S + 127) / 128);
+    for (int it = 0; it < r->n_iter; ++it) {
+        const long long i = r->iter0 + it;
+        c.iter = i;
+        c.tune = (i != 0 && i < r->burn && (i % r->tune_interval) == 0) ? 1 : 0;
+        c.count = (i <= last_tune) ? 1 : 0;
+        c.tape_z = r->tape_z ? r->tape_z + it * per_iter : nullptr;
+        c.tape_u = r->tape_u ? r->tape_u + it * per_iter : nullptr;
+        c.tape_acc = r->tape_accept ? r->tape_accept + it * per_iter : nullptr;
+        c.tr_ll = r->trace_ll ? r->trace_ll + it * per_iter : nullptr;
+        c.tr_lp = r->trace_lp ? r->trace_lp + it * per_iter : nullptr;
+        c.tr_diff = r->trace_diff ? r->trace_diff + it * per_iter : nullptr;
+        c.tr_acc = r->trace_accept ? r->trace_accept + it * per_iter : nullptr;
+        if (c.tr_ll && !(c.tr_lp && c.tr_diff && c.tr_acc)) { set_error("trace arrays go together"); return MCMCN_ERR_INVALID; }
+        for (int p = 0; p < P; ++p) {                                   // StepMethod.step, :594-597
+            c.p = p;
+            c.prior = m->prior[p];
+            complete_propose_kernel<<<nb, 128, 0, stream>>>(c);
+            if (r->timing) r->timing[3] += 1.0;
+            CK(launch_sweep(efn, g.grid, g.block, g.tile_bytes, stream, ea));
+            complete_decide_kernel<<<nb, 128, 0, stream>>>(c);
+        }
+        if (r->store && i >= r->burn && (i % r->thin) == 0) {
+            if (row >= r->store_rows) { set_error("sample store overflow at row %lld", (long long)row); return MCMCN_ERR_INVALID; }
+            const dim3 sg((unsigned)((s->n_chains + 127) / 128), (unsigned)P, 1);
+            if (r->timing) r->timing[5] += 1.0;
+            if (r->store_dtype == 64)
+                snapshot_kernel<double><<<sg, 128, 0, stream>>>(P, 1, 0, s->n_chains, S, s->theta, s->hyper, (double*)r->store + (size_t)row * P * S);
+            else
+                snapshot_kernel<float><<<sg, 128, 0, stream>>>(P, 1, 0, s->n_chains, S, s->theta, s->hyper, (float*)r->store + (size_t)row * P * S);
+            ++row;
+        }
+    }
+    CK(cudaGetLastError());
+    return MCMCN_OK;
+}
+
 }  // namespace mcmcn
 
 using namespace mcmcn;
@@ -209,6 +282,7 @@ int mcmcn_run(const mcmcn_model* m, const mcmcn_state* s, const mcmcn_run_args* 
     if (partial && m->n_groups < 2) { set_error("partial pooling needs at least 2 groups"); return MCMCN_ERR_INVALID; }
     if (partial && r->tape_z && (!r->tape_zmu || !r->tape_qsig)) { set_error("replay of partial pooling needs tape_zmu/tape_qsig"); return MCMCN_ERR_INVALID; }
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (m->pooling == MCMCN_POOL_COMPLETE && m->split && !getenv("MCMCN_NO_SPLIT")) return run_complete_split(m, s, r, stream);
 
     SweepArgs a;
     fill_args(a, ks, m, s);

@@ -131,7 +131,8 @@ class SampleStore(object):
 
 class Engine(object):
     def __init__(self, objective, nGroups, nResponsesPerGroup, pooling, nChains,
-                 priorDistribution=None, chainId0=0, seed=0, device=None, taskObsTarget=256):
+                 priorDistribution=None, chainId0=0, seed=0, device=None, taskObsTarget=256,
+                 splitMinObservations=2048):
         if not isinstance(objective, Objective):
             raise TypeError("logLikelihoodFunction must be an Objective handle (device function); "
                             "a Python callable cannot run on the GPU and there is no CPU fallback")
@@ -168,51 +169,9 @@ class Engine(object):
             raise ValueError("partial pooling needs at least 2 groups (the reference divides by nGroups - 1)")
 
         # ---- model
-        data, group_off, group_nobs, obj_const = objective.pack(stepped)
-        elem = data.dtype.itemsize
-        cap = self.lib.mcmcn_tile_capacity_bytes() // elem
-        task_group0 = [0]
-        acc_elems, acc_obs = 0, 0
-        for g in range(self.G):
-            e = int(group_off[g + 1] - group_off[g])
-            if g > task_group0[-1] and (acc_elems + e > cap or acc_obs + int(group_nobs[g]) > taskObsTarget):
-                task_group0.append(g)
-                acc_elems, acc_obs = 0, 0
-            acc_elems += e
-            acc_obs += int(group_nobs[g])
-        task_group0.append(self.G)
-        self._group_off_h = numpy.ascontiguousarray(group_off, dtype=numpy.int64)
-        self._task_group0_h = numpy.ascontiguousarray(task_group0, dtype=numpy.int32)
-        dev = self.device
-        self._data = torch.from_numpy(data).to(dev)
-        self._group_off = torch.from_numpy(self._group_off_h).to(dev)
-        self._group_nobs = torch.from_numpy(group_nobs).to(dev)
-        self._task_group0 = torch.from_numpy(self._task_group0_h).to(dev)
-        self._obj_const = torch.from_numpy(obj_const).to(dev) if obj_const is not None else None
-        tcData, tcOff = getattr(objective, "tcData", None), getattr(objective, "tcGroupOff", None)
-        self._tc_data = torch.from_numpy(tcData).to(dev) if tcData is not None else None
-        self._tc_group_off = torch.from_numpy(tcOff).to(dev) if tcData is not None else None
-
-        m = nat.Model()
-        m.objective = objective.kind
-        m.n_params = self.P
-        m.n_coef = objective.nCoef
-        m.precision = 32 if objective.precision == "fp32" else 64
-        m.pooling = nat.POOLING_CODE[pooling]
-        m.n_groups = self.G
-        m.n_tasks = len(task_group0) - 1
-        m.n_obj_const = 0 if obj_const is None else len(obj_const)
-        m.n_obs = self.nObservations
-        m.data = _ptr(self._data)
-        m.group_off = _ptr(self._group_off)
-        m.group_nobs = _ptr(self._group_nobs)
-        m.task_group0 = _ptr(self._task_group0)
-        m.task_group0_host = self._task_group0_h.ctypes.data_as(ctypes.c_void_p)
-        m.group_off_host = self._group_off_h.ctypes.data_as(ctypes.c_void_p)
-        m.obj_const = _ptr(self._obj_const)
-        m.user_objective = objective.userHandle
-        m.tc_data, m.tc_group_off = _ptr(self._tc_data), _ptr(self._tc_group_off)
-        m.tc_max_block_floats = int(numpy.diff(tcOff).max()) if tcData is not None else 0
+        m, keep = self._buildModel(stepped, pooling, taskObsTarget, tensorCore=True)
+        (self._data, self._group_off, self._group_nobs, self._task_group0, self._obj_const, self._tc_data,
+         self._tc_group_off, self._group_off_h, self._task_group0_h) = keep
         if not self.partial:
             for p, d in enumerate(priorDistribution):
                 m.prior[p] = priorFromScipy(d)
@@ -223,7 +182,7 @@ class Engine(object):
                                "into libmcmcn.so" % (m.objective, m.n_params, m.n_coef, objective.precision))
 
         # ---- chain state
-        P, G, S = self.P, self.G, self.S
+        P, G, S, dev = self.P, self.G, self.S, self.device
         f64 = torch.float64
         self.theta = torch.zeros((P, G, S), dtype=f64, device=dev)
         self.scale = torch.ones((P, G, S), dtype=f64, device=dev)            # :269
@@ -239,6 +198,71 @@ class Engine(object):
         st.theta, st.scale, st.counts = _ptr(self.theta), _ptr(self.scale), _ptr(self.counts)
         st.ll, st.lprior, st.hyper = _ptr(self.ll), _ptr(self.lprior), _ptr(self.hyper)
         self.state = st
+
+        # ---- complete pooling at scale: the same observations as groups of 128, evaluated in parallel
+        # (mcmcn_model.split); below the threshold one warp per 128 chains steps the single group
+        self._split = None
+        if pooling == "complete" and self.nObservations >= splitMinObservations:
+            N = self.nObservations
+            parts = [128] * (N // 128) + ([N % 128] if N % 128 else [])
+            sm, skeep = self._buildModel(parts, pooling, taskObsTarget, tensorCore=False)
+            scratch = torch.zeros(((P + len(parts) + 3) * S,), dtype=f64, device=dev)
+            self._split = (sm, skeep, scratch)
+            self.model.split = ctypes.addressof(sm)
+            self.model.split_scratch = _ptr(scratch)
+
+    def _buildModel(self, stepped, pooling, taskObsTarget, tensorCore):
+        """Pack the objective's observations as the groups `stepped` and describe them as a
+        mcmcn_model (include/mcmcn.h).  Returns the model and the tensors / arrays it points into."""
+        objective, dev = self.objective, self.device
+        nG = len(stepped)
+        data, group_off, group_nobs, obj_const = objective.pack(stepped)
+        elem = data.dtype.itemsize
+        cap = self.lib.mcmcn_tile_capacity_bytes() // elem
+        task_group0 = [0]
+        acc_elems, acc_obs = 0, 0
+        for g in range(nG):
+            e = int(group_off[g + 1] - group_off[g])
+            if g > task_group0[-1] and (acc_elems + e > cap or acc_obs + int(group_nobs[g]) > taskObsTarget):
+                task_group0.append(g)
+                acc_elems, acc_obs = 0, 0
+            acc_elems += e
+            acc_obs += int(group_nobs[g])
+        task_group0.append(nG)
+        group_off_h = numpy.ascontiguousarray(group_off, dtype=numpy.int64)
+        task_group0_h = numpy.ascontiguousarray(task_group0, dtype=numpy.int32)
+        d_data = torch.from_numpy(data).to(dev)
+        d_group_off = torch.from_numpy(group_off_h).to(dev)
+        d_group_nobs = torch.from_numpy(group_nobs).to(dev)
+        d_task_group0 = torch.from_numpy(task_group0_h).to(dev)
+        d_obj_const = torch.from_numpy(obj_const).to(dev) if obj_const is not None else None
+        tcData = getattr(objective, "tcData", None) if tensorCore else None
+        tcOff = getattr(objective, "tcGroupOff", None) if tensorCore else None
+        d_tc_data = torch.from_numpy(tcData).to(dev) if tcData is not None else None
+        d_tc_group_off = torch.from_numpy(tcOff).to(dev) if tcData is not None else None
+
+        m = nat.Model()
+        m.objective = objective.kind
+        m.n_params = self.P
+        m.n_coef = objective.nCoef
+        m.precision = 32 if objective.precision == "fp32" else 64
+        m.pooling = nat.POOLING_CODE[pooling]
+        m.n_groups = nG
+        m.n_tasks = len(task_group0) - 1
+        m.n_obj_const = 0 if obj_const is None else len(obj_const)
+        m.n_obs = self.nObservations
+        m.data = _ptr(d_data)
+        m.group_off = _ptr(d_group_off)
+        m.group_nobs = _ptr(d_group_nobs)
+        m.task_group0 = _ptr(d_task_group0)
+        m.task_group0_host = task_group0_h.ctypes.data_as(ctypes.c_void_p)
+        m.group_off_host = group_off_h.ctypes.data_as(ctypes.c_void_p)
+        m.obj_const = _ptr(d_obj_const)
+        m.user_objective = objective.userHandle
+        m.tc_data, m.tc_group_off = _ptr(d_tc_data), _ptr(d_tc_group_off)
+        m.tc_max_block_floats = int(numpy.diff(tcOff).max()) if tcData is not None else 0
+        return m, (d_data, d_group_off, d_group_nobs, d_task_group0, d_obj_const, d_tc_data, d_tc_group_off,
+                   group_off_h, task_group0_h)
 
     # ------------------------------------------------------------------ helpers
     @property

@@ -60,7 +60,8 @@ class Model(ctypes.Structure):
                 ("group_off_host", c_void_p), ("obj_const", c_void_p),
                 ("user_objective", c_void_p),
                 ("tc_data", c_void_p), ("tc_group_off", c_void_p), ("tc_max_block_floats", ctypes.c_int64),
-                ("prior", Prior * MAX_PARAMS)]
+                ("prior", Prior * MAX_PARAMS),
+                ("split", c_void_p), ("split_scratch", c_void_p)]
 
 
 class State(ctypes.Structure):

@@ -223,9 +223,34 @@ def test_replay_bernoulli_logit(pooling):
     assert ties64 == 0
 
 
-def test_replay_streaming_group_larger_than_tile():
+@pytest.mark.parametrize("objective", ["regression", "logit"])
+def test_replay_complete_pooling_split_over_observations(objective):
+    """Complete pooling at scale: the engine evaluates the single group of all N observations as
+    groups of 128 in parallel (mcmcn_model.split: propose / eval / decide kernels) -- same tape
+    replay criteria as the step kernels; N = 5,000 leaves a last group of 8 observations."""
+    if objective == "regression":
+        obj, names, nResp, ranges = parity.syntheticRegression(G=50, R=100, K=2)
+        prior = [scipy.stats.norm(0, 10), scipy.stats.norm(0, 10), scipy.stats.gamma(2)]
+    else:
+        obj, names, nResp, ranges = parity.syntheticLogit(G=50, R=100)
+        prior = [scipy.stats.norm(0, 5), scipy.stats.cauchy(0, 5)]
+    res = parity.replay(obj, names, 50, nResp, "complete", prior, ranges, nChains=37, nIter=60,
+                        nSamples=20, precision="fp32")
+    assert res.engine.model.split
+    err, ties = parity.checkReplay(res, 1e-5, 1e-4)
+    numpy.testing.assert_allclose(res.rows, res.oracleRows, rtol=1e-9, atol=1e-9)
+    res = parity.replay(obj, names, 50, nResp, "complete", prior, ranges, nChains=3, nIter=60,
+                        nSamples=20, precision="fp64", force=False)
+    err, ties = parity.checkReplay(res, 1e-11, 0.0)
+    assert ties == 0
+    numpy.testing.assert_allclose(res.rows, res.oracleRows, rtol=1e-9, atol=1e-9)
+
+
+def test_replay_streaming_group_larger_than_tile(monkeypatch):
     """Complete pooling makes one group of all N observations; with N beyond the shared-memory
-    tile the block is streamed through it by repeated TMA copies."""
+    tile the block is streamed through it by repeated TMA copies (the path below the split
+    threshold, forced here with MCMCN_NO_SPLIT)."""
+    monkeypatch.setenv("MCMCN_NO_SPLIT", "1")
     obj, names, nResp, ranges = parity.syntheticRegression(G=50, R=100, K=2)
     prior = [scipy.stats.norm(0, 10), scipy.stats.norm(0, 10), scipy.stats.gamma(2)]
     res = parity.replay(obj, names, 50, nResp, "complete", prior, ranges, nChains=3, nIter=40,
