@@ -1307,13 +1307,26 @@ static __global__ void __launch_bounds__(128) complete_propose_kernel(const Comp
     a.park[2 * S + c] = prior_logpdf(a.prior, prop);
 }
 
-static __global__ void __launch_bounds__(128) complete_decide_kernel(const CompleteArgs a) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.n_chains) return;
-    const size_t S = (size_t)a.S, at = (size_t)a.p * S + c;
-    double llp = 0.0;                                                   // fixed order: group 0, 1, 2, ...
+// block = (32 chains, 32 slices of the small groups): slice sums in group order, then the 32 slice
+// sums in slice order -- a fixed summation order, whatever the launch
+static __global__ void __launch_bounds__(1024) complete_decide_kernel(const CompleteArgs a) {
+    __shared__ double slice_sum[32][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;                        // < S (a multiple of 32)
+    const size_t S = (size_t)a.S;
+    {
+        const int per = (a.n_parts + 31) / 32;
+        const int g0 = min((int)threadIdx.y * per, a.n_parts), g1 = min(g0 + per, a.n_parts);
+        double sum = 0.0;
 #pragma unroll 8
-    for (int g = 0; g < a.n_parts; ++g) llp += a.part[(size_t)g * S + c];
+        for (int g = g0; g < g1; ++g) sum += a.part[(size_t)g * S + c];
+        slice_sum[threadIdx.y][threadIdx.x] = sum;
+    }
+    __syncthreads();
+    if (threadIdx.y != 0 || c >= a.n_chains) return;
+    const size_t at = (size_t)a.p * S + c;
+    double llp = 0.0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) llp += slice_sum[j][threadIdx.x];
     const double prop = a.park[c], u = a.park[S + c], lp_prop = a.park[2 * S + c];
     // Parameter.step decision tree, :334-367
     const double post_prop = lp_prop + llp;

@@ -237,7 +237,7 @@ static int run_complete_split(const mcmcn_model* m, const mcmcn_state* s, const 
             complete_propose_kernel<<<nb, 128, 0, stream>>>(c);
             if (r->timing) r->timing[3] += 1.0;
             CK(launch_sweep(efn, g.grid, g.block, g.tile_bytes, stream, ea));
-            complete_decide_kernel<<<nb, 128, 0, stream>>>(c);
+            complete_decide_kernel<<<(unsigned)(S / 32), dim3(32, 32, 1), 0, stream>>>(c);
         }
         if (r->store && i >= r->burn && (i % r->thin) == 0) {
             if (row >= r->store_rows) { set_error("sample store overflow at row %lld", (long long)row); return MCMCN_ERR_INVALID; }
