@@ -81,13 +81,20 @@ __device__ __forceinline__ uint4 philox_draw(long long chain_id, unsigned long l
     const uint2 key = make_uint2((unsigned)chain_id ^ (unsigned)(seed >> 32) * 0x9E3779B1u, (unsigned)seed ^ (unsigned)(chain_id >> 32));
     return philox4x32_10(ctr, key);
 }
+// log2 of a positive normal float on the MUFU unit (no denormal rescue: the arguments here are
+// uniforms >= 2^-33)
+__device__ __forceinline__ float lg2_fast(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 // standard normal from two 32-bit words (Box-Muller at fp32 resolution, branch-free on the MUFU
 // unit: lg2, sqrt, cos; symmetric about 0, |z| <= 5.8)
 __device__ __forceinline__ double normal_from(unsigned a, unsigned b) {
     const float u1 = (float)((a >> 8) + 1u) * 5.9604644775390625e-8f;   // (0, 1]
     const float u2 = (float)(b >> 8) * 5.9604644775390625e-8f;          // [0, 1)
     float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * lg2_fast(u1)));   // -2 ln u1
     return (double)(r * __cosf(6.283185307179586f * u2));
 }
 // Both Box-Muller branches of the same two words: one Philox call serves two consecutive sweeps
@@ -96,7 +103,7 @@ __device__ __forceinline__ void normal_pair_from(unsigned a, unsigned b, float& 
     const float u1 = (float)((a >> 8) + 1u) * 5.9604644775390625e-8f;   // (0, 1]
     const float u2 = (float)(b >> 8) * 5.9604644775390625e-8f;          // [0, 1)
     float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * lg2_fast(u1)));   // -2 ln u1
     zc = r * __cosf(6.283185307179586f * u2);
     zs = r * __sinf(6.283185307179586f * u2);
 }
@@ -111,7 +118,7 @@ __device__ __forceinline__ double uniform_from32(unsigned w) {
 // (float)u adds 6e-8 relative, so |__logf((float)u) - log(u)| < 1e-6 * (1 + |log u|) with a
 // wide margin; rounding diff to FP32 moves it by at most 6e-8 relative.
 __device__ __forceinline__ int log_u_vs_diff_fast(double u, double diff) {
-    const float lu = __logf((float)u);
+    const float lu = 0.6931471805599453f * lg2_fast((float)u);
     const float tol = 1e-6f * (1.0f + fabsf(lu));
     const float d = (float)diff;
     const float dtol = 1.2e-7f * fabsf(d);
@@ -697,6 +704,8 @@ struct SweepArgs {
     double* ll;
     double* lprior;
     const double* hyper;
+    const double* hyper_lsd;      // hyper + 3 P S (log sd) and hyper + 4 P S (1 / sd): bases formed on the host
+    const double* hyper_isd;
     // iteration
     long long iter;
     unsigned long long seed;

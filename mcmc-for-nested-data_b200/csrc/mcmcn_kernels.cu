@@ -117,6 +117,8 @@ static int fill_args(SweepArgs& a, const KernelSet* ks, const mcmcn_model* m, co
     a.ll = s->ll;
     a.lprior = s->lprior;
     a.hyper = s->hyper;
+    a.hyper_lsd = s->hyper ? s->hyper + (size_t)3 * m->n_params * s->stride : nullptr;
+    a.hyper_isd = s->hyper ? s->hyper + (size_t)4 * m->n_params * s->stride : nullptr;
     a.tc_data = m->tc_data;
     a.tc_group_off = reinterpret_cast<const long long*>(m->tc_group_off);
     return MCMCN_OK;

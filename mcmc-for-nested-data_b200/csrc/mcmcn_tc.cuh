@@ -94,6 +94,9 @@ __device__ __forceinline__ unsigned tf32_rn(float v) { return (__float_as_uint(v
 __device__ __forceinline__ void tmem_st1(unsigned addr, unsigned v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(addr), "r"(v) : "memory");
 }
+__device__ __forceinline__ void tmem_st2(unsigned addr, unsigned v0, unsigned v1) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v0), "r"(v1) : "memory");
+}
 // D[tmem] (+)= A[smem descriptor] . B[smem descriptor], kind::tf32, one CTA
 __device__ __forceinline__ void mma_tf32_ss(unsigned d, unsigned long long adesc, unsigned long long bdesc, unsigned idesc,
                                             unsigned accumulate) {
@@ -187,8 +190,8 @@ __device__ __forceinline__ void tc_fetch_state(TcInputs& o, const SweepArgs& a, 
     o.bbar = p < P - 1 ? a.obj_const[bb] : 0.0;
     if (partial) {
         o.h_mu = a.hyper[hy];
-        o.h_lsd = a.hyper[3 * PS + hy];
-        o.h_isd = a.hyper[4 * PS + hy];
+        o.h_lsd = a.hyper_lsd[hy];
+        o.h_isd = a.hyper_isd[hy];
         if (GENERAL && override_lp) o.lp_cur = a.lprior[at];
     } else {
         o.lp_cur = a.lprior[at];
@@ -212,6 +215,20 @@ __device__ __forceinline__ void tc_fetch_random(TcInputs& o, const SweepArgs& a,
         o.z = stash.z;
         o.u = stash.u;
     }
+}
+
+// LinReg::Aux of a sigma: m = -1/(2 sigma^2), r = R (log sigma + log sqrt(2 pi)); sigma <= 0 -> nan (scipy).
+// FP32 reciprocal and logarithm (1 ulp each: 1e-7 relative on the log-likelihood) in place of about
+// 60 FP64 instructions for the division and the logarithm: 0.2855 -> 0.2781 ms per C3 launch.
+__device__ __forceinline__ void tc_sigma_terms(double sigma, int R, double& m, double& r) {
+    const float sf = (float)sigma;
+    if (!(sf > 0.0f)) {
+        m = r = __longlong_as_double(0x7ff8000000000000LL);
+        return;
+    }
+    const double inv = (double)__frcp_rn(sf);
+    m = -0.5 * inv * inv;
+    r = (double)R * ((double)logf(sf) + MCMCN_LOG_SQRT_2PI);
 }
 
 // CTA-wide rendezvous before an MMA issue: every lane's tensor-memory traffic (tcgen05.st of the
@@ -310,16 +327,24 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
         TcInputs in;
         tc_fetch_state<GENERAL>(in, a, 0, at, hy, bb, partial, override_lp);
         tc_fetch_random<GENERAL>(in, a, 0, g, chl, at, replay, stash);
+        const double* tg = a.theta + at;                               // (name 0, group g, this chain); name k is k * GS further
         if (g + 1 < g1) {                                              // next group's state: DRAM -> L2 meanwhile
-            for (int k = 0; k < P; ++k)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.theta + ((size_t)k * a.G + g + 1) * S + chl));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ll + (size_t)(g + 1) * S + chl));
+            const double* pf = tg + S;
+            for (int k = 0; k < P; ++k, pf += GS) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ll + at + S));
         }
+        // The proposal of a sweep and its centred FP32 value are formed at the end of the sweep before
+        // (here: for sweep 0), so that column p (the value kept) and column p + 1 (the next proposal) of
+        // the A operand go out in one two-column store.
+        double prop = __dadd_rn(in.cur, __dmul_rn(in.sc, in.z));      // numpy.random.normal(value, sd), :304-306
+        float wcur = (float)__dsub_rn(in.cur, in.bbar), wprop = (float)__dsub_rn(prop, in.bbar);
         {   // A operand of the current state: centred coefficients (FP32), split hi / lo
             unsigned hi[8], lo[8];
+            const double* tk = tg;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float b = k < K ? (float)__dsub_rn(a.theta[((size_t)k * a.G + g) * S + chl], bbar[k]) : 0.0f;
+            for (int k = 0; k < 8; ++k, tk += GS) {
+                float b = k < K ? (float)__dsub_rn(*tk, bbar[k]) : 0.0f;
+                if (k == 0) b = wprop;                                 // column 0 already holds sweep 0's proposal
                 hi[k] = tf32_rn(b);
                 lo[k] = tf32_rn(b - __uint_as_float(hi[k]));
             }
@@ -327,27 +352,18 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
             tmem_st8(tlane + MCMCN_TC_A_LO, lo);
         }
         double aux_m, aux_r;                                           // LinReg::Aux of the current sigma
-        {
-            const double sg = (double)(float)a.theta[((size_t)K * a.G + g) * S + chl];
-            if (!(sg > 0.0)) {
-                aux_m = aux_r = __longlong_as_double(0x7ff8000000000000LL);
-            } else {
-                const double inv = 1.0 / sg;
-                aux_m = -0.5 * inv * inv;
-                aux_r = (double)R * (log(sg) + MCMCN_LOG_SQRT_2PI);
-            }
-        }
-        double ll_cur = a.ll[(size_t)g * S + chl];
+        tc_sigma_terms(tg[(size_t)K * GS], R, aux_m, aux_r);
+        double ll_cur = a.ll[at];
         mbar_wait(mb_tma0 + 8u * s, (tma_phase >> s) & 1u);
         tma_phase ^= 1u << s;
 
 #pragma unroll 1
         for (int p = 0; p < P; ++p, at += GS, hy += S, ++bb) {
             const bool is_sigma = p == K;
-            // proposal and log-priors (pure functions of state known before the sweep; the reference
-            // evaluates them after the likelihood, :335, :331).  (Moving the priors or the random numbers
+            // log-priors of the proposal (formed at the end of the sweep before) and of the current value
+            // (pure functions of state known before the sweep; the reference evaluates them after the
+            // likelihood, :335, :331).  (Moving the priors or the random numbers
             // behind the MMAs instead measured 7-10 % slower, twice.)
-            const double prop = __dadd_rn(in.cur, __dmul_rn(in.sc, in.z));     // numpy.random.normal(value, sd), :304-306
             double lp_prop, lp_cur;
             if (partial) {
                 lp_prop = norm_logpdf_inv(prop, in.h_mu, in.h_isd, in.h_lsd);
@@ -358,23 +374,8 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
             }
             const double u = in.u;
             double m_prop = aux_m, r_prop = aux_r;
-            float wcur = 0.0f, wprop = 0.0f;
-            if (is_sigma) {                                            // LinReg::aux of the proposed sigma
-                const double sg = (double)(float)prop;
-                if (!(sg > 0.0)) {                                     // scipy: scale <= 0 -> nan
-                    m_prop = r_prop = __longlong_as_double(0x7ff8000000000000LL);
-                } else {
-                    const double inv = 1.0 / sg;
-                    m_prop = -0.5 * inv * inv;
-                    r_prop = (double)R * (log(sg) + MCMCN_LOG_SQRT_2PI);
-                }
-            } else {                                                   // column p of the A operand <- the proposal
-                wcur = (float)__dsub_rn(in.cur, in.bbar);
-                wprop = (float)__dsub_rn(prop, in.bbar);
-                const unsigned h = tf32_rn(wprop);
-                tmem_st1(tlane + MCMCN_TC_A_HI + p, h);
-                tmem_st1(tlane + MCMCN_TC_A_LO + p, tf32_rn(wprop - __uint_as_float(h)));
-            }
+            const float wcur_now = wcur, wprop_now = wprop;            // this sweep's; wcur / wprop move on to the next below
+            if (is_sigma) tc_sigma_terms(prop, R, m_prop, r_prop);     // LinReg::aux of the proposed sigma
             tmem_wait_st();
             if (tc_rendezvous_issuer()) tc_issue_chunk(tbase, stage, ones, np, 0, mb_mma);
             // while the tensor core works: state and random numbers of the next sweep.  (Drawing the
@@ -425,11 +426,20 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
                 aux_m = m_prop;
                 aux_r = r_prop;
             }
-            if (!is_sigma) {                                           // column p <- the value the chain keeps
-                const float wkeep = accept ? wprop : wcur;
-                const unsigned h = tf32_rn(wkeep);
-                tmem_st1(tlane + MCMCN_TC_A_HI + p, h);
-                tmem_st1(tlane + MCMCN_TC_A_LO + p, tf32_rn(wkeep - __uint_as_float(h)));
+            if (!is_sigma) {                                           // column p <- the value the chain keeps, column p + 1 <- the next proposal
+                const float wkeep = accept ? wprop_now : wcur_now;
+                const unsigned h = tf32_rn(wkeep), l = tf32_rn(wkeep - __uint_as_float(h));
+                prop = __dadd_rn(in.cur, __dmul_rn(in.sc, in.z));      // `in` holds sweep p + 1 by now
+                if (p + 1 < K) {
+                    wcur = (float)__dsub_rn(in.cur, in.bbar);
+                    wprop = (float)__dsub_rn(prop, in.bbar);
+                    const unsigned nh = tf32_rn(wprop);
+                    tmem_st2(tlane + MCMCN_TC_A_HI + p, h, nh);
+                    tmem_st2(tlane + MCMCN_TC_A_LO + p, l, tf32_rn(wprop - __uint_as_float(nh)));
+                } else {                                               // the next sweep is sigma's: no column of its own
+                    tmem_st1(tlane + MCMCN_TC_A_HI + p, h);
+                    tmem_st1(tlane + MCMCN_TC_A_LO + p, l);
+                }
             }
             if (count && on) {
                 unsigned cnt = a.counts[at];
