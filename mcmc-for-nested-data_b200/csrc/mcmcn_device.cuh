@@ -119,10 +119,12 @@ __device__ __forceinline__ double uniform_from32(unsigned w) {
 // wide margin; rounding diff to FP32 moves it by at most 6e-8 relative.
 __device__ __forceinline__ int log_u_vs_diff_fast(double u, double diff) {
     const float lu = 0.6931471805599453f * lg2_fast((float)u);
-    const float tol = 1e-6f * (1.0f + fabsf(lu));
     const float d = (float)diff;
-    const float dtol = 1.2e-7f * fabsf(d);
-    return (d - dtol > lu + tol) ? 1 : ((d + dtol < lu - tol) ? -1 : 0);
+    // one margin for both sides: 2e-6 (1 + |log u|) + 2.4e-7 |diff| covers the errors above and the
+    // rounding of the FP32 difference itself
+    const float x = d - lu;
+    const float m = fmaf(fabsf(d), 2.4e-7f, fmaf(fabsf(lu), 2e-6f, 2e-6f));
+    return (x > m) ? 1 : ((x < -m) ? -1 : 0);
 }
 // uniform in [0,1) with 53 random bits, numpy's recipe (legacy random_sample)
 __device__ __forceinline__ double uniform_from(unsigned a, unsigned b) {

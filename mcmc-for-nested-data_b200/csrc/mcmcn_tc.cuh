@@ -144,6 +144,20 @@ __device__ __forceinline__ double tc_sum_squares_fixed(unsigned addr) {
     }
     return (double)((sum2(s[0]) + sum2(s[1])) + (sum2(s[2]) + sum2(s[3])));
 }
+// The same with the four FP32 pair accumulators kept by the caller (they carry over both chunks of a
+// 208-observation group: 26 terms each before the one fold into FP64).
+template <int PIECES>
+__device__ __forceinline__ void tc_accumulate_fixed(unsigned addr, f32x2 (&s)[4]) {
+    unsigned v[2][16];
+    tmem_ld16(addr, v[0]);
+    tmem_wait_ld(v[0]);
+#pragma unroll
+    for (int j = 0; j < PIECES; ++j) {
+        if (j + 1 < PIECES) tmem_ld16(addr + 16 * (j + 1), v[(j + 1) & 1]);
+        MCMCN_TC_CONSUME(v[j & 1], s)
+        if (j + 1 < PIECES) tmem_wait_ld(v[(j + 1) & 1]);
+    }
+}
 __device__ __forceinline__ double tc_sum_squares_any(unsigned addr, int pieces) {
     f32x2 s[4] = {0ull, 0ull, 0ull, 0ull};
     unsigned va[16];
@@ -387,6 +401,17 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
             }
 
             double acc = 0.0;
+            if (np == 208) {                                           // 112 + 96 observations (C3's groups): straight line, one fold
+                f32x2 sq[4] = {0ull, 0ull, 0ull, 0ull};
+                mbar_wait(mb_mma, mma_phase);
+                tc_fence_after();
+                tc_accumulate_fixed<7>(tlane + MCMCN_TC_D, sq);
+                if (tc_rendezvous_issuer()) tc_issue_chunk(tbase, stage, ones, np, 1, mb_mma);
+                mbar_wait(mb_mma, mma_phase ^ 1u);
+                tc_fence_after();
+                tc_accumulate_fixed<6>(tlane + MCMCN_TC_D, sq);
+                acc = (double)((sum2(sq[0]) + sum2(sq[1])) + (sum2(sq[2]) + sum2(sq[3])));
+            } else
             for (int c = 0; c < nchunks; ++c) {
                 mbar_wait(mb_mma, mma_phase);
                 mma_phase ^= 1u;
