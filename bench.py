@@ -444,9 +444,9 @@ def main():
     ap.add_argument("--pooling", default="partial", choices=["partial", "none"],
                     help="partial (default, the BASELINE metric's mode) or none (BASELINE config 5 names both)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--traffic", type=float, default=208.0e6,
+    ap.add_argument("--traffic", type=float, default=199.9e6,
                     help="dram__bytes_read.sum + dram__bytes_write.sum per step-kernel launch, from the committed "
-                         "ncu --set full capture (profiles/r1_tc_kernel_ncu_summary.txt); not measured live")
+                         "ncu --set full capture (profiles/r1_final_tc_kernel_ncu_summary.txt); not measured live")
     ap.add_argument("--traffic-pipe", type=float, default=204.2e6,
                     help="same for the FP32-pipe kernel (profiles/r1_sweep_kernel_ncu_summary.txt)")
     args = ap.parse_args()
