@@ -1221,8 +1221,24 @@ __global__ void __launch_bounds__(32 * NS) hyper_onepass_kernel(const HyperArgs 
     if (on) {
         c = a.hyper[((size_t)0 * a.P + p) * S + ch];
         if (!finite64(c)) c = th[0];
-        for (int g = ty; g < a.G; g += NS) {
-            const double d = th[(size_t)g * S] - c;
+        // eight loads in flight per thread (a thread reads only G / NS values: without the unroll the
+        // loop is one L2 / DRAM latency per value); the sums keep their order
+        const double* tq = th + (size_t)ty * S;
+        const size_t step = (size_t)NS * S;
+        int g = ty;
+        for (; g + 7 * NS < a.G; g += 8 * NS, tq += 8 * step) {
+            double v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = tq[(size_t)k * step];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const double d = v[k] - c;
+                s1 += d;
+                s2 = fma(d, d, s2);
+            }
+        }
+        for (; g < a.G; g += NS, tq += step) {
+            const double d = *tq - c;
             s1 += d;
             s2 = fma(d, d, s2);
         }
@@ -1262,9 +1278,6 @@ __global__ void __launch_bounds__(32 * NS) hyper_onepass_kernel(const HyperArgs 
     }
 }
 
-// ---------------------------------------------------------------- retained-sample write-back
-// One row of StepMethod.values (:648-654, :780-787): per name [mu, sigma2 (partial)], theta[0..G-1].
-// store[(row*ncol + col)*S + chain]; a warp writes 32 consecutive chains.
 // ---------------------------------------------------------------- complete pooling, split over observations
 // One group of all N observations (CompletePooling, posteriorSampling.py:662-685) leaves only the
 // chains to parallelise over in the step kernel.  When the host provides the same observations as
@@ -1385,6 +1398,9 @@ static __global__ void __launch_bounds__(1024) complete_decide_kernel(const Comp
     }
 }
 
+// ---------------------------------------------------------------- retained-sample write-back
+// One row of StepMethod.values (:648-654, :780-787): per name [mu, sigma2 (partial)], theta[0..G-1].
+// store[(row*ncol + col)*S + chain]; a warp writes 32 consecutive chains.
 template <typename TS>
 __global__ void snapshot_kernel(int P, int G, int partial, int n_chains, int S, const double* theta,
                                 const double* hyper, TS* store_row) {
