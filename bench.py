@@ -268,6 +268,7 @@ def runGpu(args):
         raise RuntimeError("bench.py needs a CUDA device (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version banner goes to stderr: stdout is the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
