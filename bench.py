@@ -189,7 +189,7 @@ def runReference(args):
                              "sample": "%d chains (one per host core) x %d iterations per step of the same "
                                        "workload, numpy restatement of the reference (oracle/)" % (cores, iters)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 def workloadConfig(args, chains):
@@ -268,7 +268,6 @@ def runGpu(args):
         raise RuntimeError("bench.py needs a CUDA device (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version banner goes to stderr: stdout is the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
@@ -418,12 +417,24 @@ def runGpu(args):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": "1 chain x %d iterations of the same workload (%.1f s), numpy "
                                               "restatement of the reference (oracle/)" % (args.cpu_iters, dt)}
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(text):
+    """The one JSON line, on the process's real stdout."""
+    if _REAL_STDOUT is None:
+        print(text, flush=True)
+    else:
+        os.write(_REAL_STDOUT, (text + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -451,6 +462,11 @@ def main():
     ap.add_argument("--traffic-pipe", type=float, default=204.2e6,
                     help="same for the FP32-pipe kernel (profiles/r1_sweep_kernel_ncu_summary.txt)")
     args = ap.parse_args()
+    # Everything libraries print on file descriptor 1 (NCCL's version banner under NCCL_DEBUG=VERSION,
+    # for one) goes to stderr; stdout carries the JSON line and nothing else.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.workload == "c5":
         args.groups, args.obs, args.coef, args.chains_per_gpu = 10000, 50, 0, 4096
         args.iters_per_step, args.thin = min(args.iters_per_step, 20), max(args.thin, 20)
