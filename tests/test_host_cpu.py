@@ -114,6 +114,29 @@ def test_regression_packing_is_the_same_residual():
         assert list(nobs) == nResp and off[-1] == data.size
 
 
+def test_split_packing_of_complete_pooling_is_the_same_sum_of_squares():
+    """Complete pooling at scale packs the observations twice (Engine: mcmcn_model.split): as the
+    one stepped group and as groups of 128.  Both packings must give the same residual sum of
+    squares for any coefficient vector (each group is centred on its own least-squares fit)."""
+    from objectives import Objective
+    rs = numpy.random.RandomState(1)
+    N, K = 300, 3
+    X, y = rs.normal(size=(N, K)), 50 + rs.normal(size=N)
+    obj = Objective.linear_regression(X, y, "fp64")
+    b = rs.normal(size=K)
+    want = float(numpy.sum((X @ b - y) ** 2))
+    for stepped in ([N], [128, 128, 44]):
+        data, off, nobs, bbar = obj.pack(stepped)
+        bbar = bbar.reshape(len(stepped), K)
+        unit, total = 4 * 4 + 4, 0.0
+        for g in range(len(stepped)):
+            blk = data[off[g]:off[g + 1]].reshape(-1, unit)
+            res = numpy.einsum("qkj,k->qj", blk[:, :16].reshape(-1, 4, 4)[:, :K, :], b - bbar[g]) + blk[:, 16:]
+            total += float(numpy.sum(res ** 2))
+        assert abs(total - want) <= 1e-9 * want
+        assert int(nobs.sum()) == N
+
+
 def test_tensor_core_operand_blocks_are_an_exact_3xtf32_split():
     """mcmcn_model.tc_data (include/mcmcn.h): per group [X_hi | X_lo | NE] in the K-major core-matrix
     layout; every part must be exact in TF32 (13 zero low bits) and the parts must add up to the
