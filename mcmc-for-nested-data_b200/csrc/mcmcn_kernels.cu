@@ -132,6 +132,17 @@ static bool tc_eligible(const mcmcn_model* m) {
            m->tc_group_off && m->tc_max_block_floats > 0 && m->tc_max_block_floats * 4 <= kTcStageCapBytes &&
            !getenv("MCMCN_NO_TC");
 }
+// Does every group pad to 208 observations in the tensor-core blocks (193-208 observations)?  Read off
+// the host copy of the FP32-pipe block table: a linear-regression block is ceil(R / 4) quads of
+// 4 * KP + 4 elements.
+static bool tc_uniform208(const mcmcn_model* m) {
+    const long long unit = 4LL * ((m->n_coef + 3) & ~3) + 4;
+    for (int g = 0; g < m->n_groups; ++g) {
+        const long long quads = (m->group_off_host[g + 1] - m->group_off_host[g]) / unit;
+        if (quads < 49 || quads > 52) return false;
+    }
+    return true;
+}
 static Geometry tc_geometry(const mcmcn_model* m, int n_chains, int* stage_bytes, int* stages) {
     Geometry g;
     const int ncb = (n_chains + 127) / 128;
@@ -305,9 +316,10 @@ int mcmcn_run(const mcmcn_model* m, const mcmcn_state* s, const mcmcn_run_args* 
         fprintf(stderr, "mcmcn_run: tc=%d fast=%d wide=%d all_fit=%d tape=%p trace=%p force=%p override=%d partial=%d smem=%zu grid=(%u,%u) block=%u\n",
                 (int)tc, (int)fast, (int)g.wide, (int)g.all_fit, (const void*)r->tape_z, (void*)r->trace_ll, (const void*)r->tape_accept,
                 r->use_lprior_override, (int)partial, g.smem, g.grid.x, g.grid.y, g.block.x);
-    const sweep_fn general = tc ? tc_sweep_kernel(-1) : (g.wide ? ks->sweep_wide : ks->sweep_one);
+    const bool u208 = tc && tc_uniform208(m);
+    const sweep_fn general = tc ? tc_sweep_kernel(-1, u208) : (g.wide ? ks->sweep_wide : ks->sweep_one);
     sweep_fn fast_fn[4];
-    for (int f = 0; f < 4; ++f) fast_fn[f] = tc ? tc_sweep_kernel(f) : ks->sweep_fast[f];
+    for (int f = 0; f < 4; ++f) fast_fn[f] = tc ? tc_sweep_kernel(f, u208) : ks->sweep_fast[f];
     rc = set_smem_attr((const void*)general, g.smem);
     for (int f = 0; f < 4 && !rc; ++f) rc = set_smem_attr((const void*)fast_fn[f], g.smem);
     if (rc) return rc;

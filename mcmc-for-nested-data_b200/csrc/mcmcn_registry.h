@@ -36,6 +36,6 @@ const KernelSet* sets_linreg_d(int* n);
 const KernelSet* sets_linreg_e(int* n);
 const KernelSet* sets_logit(int* n);
 const KernelSet* sets_gauss(int* n);
-sweep_fn tc_sweep_kernel(int f);    // mcmcn_sets_tc.cu
+sweep_fn tc_sweep_kernel(int f, bool uniform208);    // mcmcn_sets_tc.cu
 
 }  // namespace mcmcn

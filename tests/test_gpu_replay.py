@@ -91,6 +91,8 @@ def test_replay_c3_shape_wide_path(precision, tol, tensorCore, monkeypatch):
     (4, 112, 8, False, "none", 1),           # exactly one full chunk, fixed priors, a single chain
     (7, 200, 5, False, "partial", 257),      # three chain blocks, the last with one chain
     (3, 500, 8, False, "partial", 40),       # 48 KB blocks: one TMA stage, five accumulator chunks
+    (4, 160, 8, False, "partial", 70),       # two chunks of 112 + 48: the straight-line read-back with a looped second chunk
+    (5, 205, 3, True, "partial", 33),        # ragged groups of 1..409 observations: one, two and more chunks side by side
 ])
 def test_replay_tensor_core_kernel_shapes(G, R, K, ragged, pooling, nChains):
     """The tcgen05 step kernel over the shapes that change its control flow: number of
