@@ -191,6 +191,7 @@ struct TcInputs {
     double bbar;                    // reference point of this coefficient (0 for sigma)
     double h_mu, h_lsd, h_isd;      // partial pooling: this name's hyper-parameters
     double lp_cur;                  // fixed priors / log-prior override: stored log-prior of the current value
+    unsigned cnt;                   // burn-in: accepted | rejected << 16 since the last tune, fetched with the rest (not after the decision)
 };
 
 // One Philox4x32-10 call serves two consecutive sweeps: Box-Muller turns words 0-1 into two
@@ -203,8 +204,9 @@ struct TcStash { double z, u; };
 // State loads and random numbers are separate so that they can sit behind different MMAs.
 template <bool GENERAL>
 __device__ __forceinline__ void tc_fetch_state(TcInputs& o, const SweepArgs& a, int p, size_t at, size_t hy, size_t bb,
-                                               bool partial, bool override_lp) {
+                                               bool partial, bool override_lp, bool count = false) {
     const int P = a.P;
+    o.cnt = count ? a.counts[at] : 0u;
     const size_t PS = (size_t)P * (size_t)a.S;
     o.cur = a.theta[at];
     o.sc = a.scale[at];
@@ -351,7 +353,7 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
         const size_t GS = (size_t)a.G * S;
         size_t at = (size_t)g * S + chl, hy = (size_t)chl, bb = (size_t)g * K;   // sweep 0; bumped by GS / S / 1 per sweep
         TcInputs in;
-        tc_fetch_state<GENERAL>(in, a, 0, at, hy, bb, partial, override_lp);
+        tc_fetch_state<GENERAL>(in, a, 0, at, hy, bb, partial, override_lp, count);
         tc_fetch_random<GENERAL>(in, a, 0, g, chl, at, replay, stash);
         const double* tg = a.theta + at;                               // (name 0, group g, this chain); name k is k * GS further
         if (g + 1 < g1) {                                              // next group's state: DRAM -> L2 meanwhile
@@ -399,6 +401,7 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
                 lp_cur = in.lp_cur;
             }
             const double u = in.u;
+            const unsigned cnt_now = in.cnt;
             double m_prop = aux_m, r_prop = aux_r;
             const float wcur_now = wcur, wprop_now = wprop;            // this sweep's; wcur / wprop move on to the next below
             if (is_sigma) tc_sigma_terms(prop, R, m_prop, r_prop);     // LinReg::aux of the proposed sigma
@@ -408,7 +411,7 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
             // random numbers inside the read-back code instead, to fill its tensor-memory latency, cost
             // registers and measured 8 % slower.)
             if (p + 1 < P) {
-                tc_fetch_state<GENERAL>(in, a, p + 1, at + GS, hy + S, bb + 1, partial, override_lp);
+                tc_fetch_state<GENERAL>(in, a, p + 1, at + GS, hy + S, bb + 1, partial, override_lp, count);
                 tc_fetch_random<GENERAL>(in, a, p + 1, g, chl, at + GS, replay, stash);
             }
 
@@ -489,7 +492,7 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
                 }
             }
             if (count && on) {
-                unsigned cnt = a.counts[at];
+                unsigned cnt = cnt_now;
                 cnt += accept ? 1u : 0x10000u;
                 if (a.tune) {                                          // Parameter.tune, :385-437
                     const unsigned na = cnt & 0xFFFFu, nrj = cnt >> 16;
