@@ -852,6 +852,10 @@ __global__ void __launch_bounds__(MAXT, MINB) sweep_kernel(const SweepArgs a) {
                     cur[c] = a.theta[row + chl[c]];
                     sc[c] = a.scale[row + chl[c]];
                 }
+                if (count) {                                           // burn-in: the counters are read after the decision -- have them in L1 by then
+#pragma unroll
+                    for (int c = 0; c < C; ++c) prefetch_l1(a.counts + row + chl[c]);
+                }
                 if (p + 1 < P) {                                       // next sweep's state into L1 meanwhile
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
