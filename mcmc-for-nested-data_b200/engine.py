@@ -10,6 +10,7 @@ Reference symbols this module stands in for (``/root/reference/posteriorSampling
 """
 
 import ctypes
+import os
 import math
 
 import numpy
@@ -325,6 +326,18 @@ class Engine(object):
         if pooledTheta is not None:
             pt = torch.zeros((self.P, self.S), dtype=torch.float64, device=self.device)
             self._up(pt, pooledTheta)
+        if self._split is not None and not os.environ.get("MCMCN_NO_SPLIT"):
+            # complete pooling at scale: evaluate over the groups of 128 in parallel and add them up in
+            # group order (the single stepped group's current values are themselves a pooled vector);
+            # the start-state search and the MLE start call this hundreds of times
+            sm = self._split[0]
+            if pt is None:
+                pt = self.theta[:, 0, :].contiguous()
+            parts = torch.zeros((sm.n_groups, self.S), dtype=torch.float64, device=self.device)
+            nat.call("mcmcn_group_loglik", ctypes.byref(sm), ctypes.byref(self.state), _ptr(pt), _ptr(parts), self.stream)
+            nll = torch.zeros((self.S,), dtype=torch.float64, device=self.device)
+            nat.call("mcmcn_pooled_nll", int(sm.n_groups), self.S, _ptr(parts), _ptr(nll), self.stream)
+            return nll.neg_().reshape(1, self.S)
         nat.call("mcmcn_group_loglik", ctypes.byref(self.model), ctypes.byref(self.state),
                  _ptr(pt), _ptr(out), self.stream)
         return out

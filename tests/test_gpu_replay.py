@@ -248,6 +248,30 @@ def test_replay_complete_pooling_split_over_observations(objective):
     numpy.testing.assert_allclose(res.rows, res.oracleRows, rtol=1e-9, atol=1e-9)
 
 
+@pytest.mark.parametrize("precision,tol", [("fp64", 1e-12), ("fp32", 1e-5)])
+def test_complete_pooling_loglik_split_equals_single_group(precision, tol, monkeypatch):
+    """The log-likelihood the start-state search and the MLE start evaluate under complete pooling:
+    summed over groups of 128 (split) it must equal the single group of all N observations, for the
+    current state and for an explicit pooled vector."""
+    from engine import Engine
+    obj, names, nResp, ranges = parity.syntheticRegression(G=40, R=77, K=3)
+    prior = [scipy.stats.norm(0, 10)] * 3 + [scipy.stats.gamma(2)]
+    eng = Engine(parity.deviceObjective(obj, nResp, precision), 40, nResp, "complete", 9, priorDistribution=prior, seed=2)
+    assert eng.model.split
+    rs = numpy.random.RandomState(4)
+    theta = rs.normal(size=(4, 1, 9))
+    theta[3] = 0.5 + rs.random_sample((1, 9))
+    eng.setState(theta, numpy.zeros((1, 9)), numpy.zeros((4, 1, 9)))
+    pooled = rs.normal(size=(4, 9))
+    pooled[3] = 1.0 + rs.random_sample(9)
+    got = [eng.groupLogLikelihood()[0, :9].cpu().numpy(), eng.groupLogLikelihood(pooled)[0, :9].cpu().numpy(), eng.pooledNll(pooled)]
+    monkeypatch.setenv("MCMCN_NO_SPLIT", "1")
+    want = [eng.groupLogLikelihood()[0, :9].cpu().numpy(), eng.groupLogLikelihood(pooled)[0, :9].cpu().numpy(), eng.pooledNll(pooled)]
+    for g, w in zip(got, want):
+        assert numpy.isfinite(w).all()
+        assert parity.relErr(g, w).max() <= tol
+
+
 def test_replay_streaming_group_larger_than_tile(monkeypatch):
     """Complete pooling makes one group of all N observations; with N beyond the shared-memory
     tile the block is streamed through it by repeated TMA copies (the path below the split
