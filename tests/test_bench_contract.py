@@ -1,0 +1,47 @@
+"""The driver-facing contract of bench.py: ONE JSON line on stdout with the agreed keys, for the
+reference arm (CPU, runs everywhere) and for the GPU arm."""
+
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+             "scaling", "vs_baseline", "dtype", "data", "config", "e2e"}
+
+
+def _run(args, timeout):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, cwd=ROOT, timeout=timeout,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, "stdout must carry exactly one line, got %d" % len(lines)
+    return json.loads(lines[0])
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    d = _run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-iters", "5"], 600)
+    assert BASE_KEYS <= set(d)
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["metric"] == "chain-iterations/sec" and d["value"] > 0
+    assert d["config"]["workload"].startswith("C3")
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+@pytest.mark.gpu
+def test_gpu_arm_prints_one_json_line_with_roofline_and_e2e():
+    d = _run(["--steps", "2", "--warmup", "3", "--no-cpu-baseline"], 600)
+    assert BASE_KEYS <= set(d) and "impl" not in d
+    assert d["n_gpus"] == 1 and d["dtype"] == "f32" and d["data"] == "synthetic" and d["value"] > 1e5
+    assert d["gpu_launches"] > 0
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] != d["value"]
+    r = d["roofline"]
+    assert r["bound"] in ("tensor", "fp32", "mufu") and r["unit"] in ("TFLOP/s", "Gop/s")
+    assert 0 < r["frac"] < 1 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] > 0
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
