@@ -33,6 +33,14 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
+def test_reference_arm_other_ranks_exit_quietly():
+    """Under torchrun (N > 1) rank 0 alone runs the reference arm; the other ranks exit 0 without work."""
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], cwd=ROOT,
+                       timeout=120, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
 @pytest.mark.gpu
 def test_gpu_arm_prints_one_json_line_with_roofline_and_e2e():
     d = _run(["--steps", "2", "--warmup", "3", "--no-cpu-baseline"], 600)
