@@ -207,8 +207,8 @@ __device__ __forceinline__ double prior_logpdf(const mcmcn_prior& pr, double x) 
             r = __dsub_rn(__dadd_rn(t1, t2), pr.c0);
             break;
         }
-        case MCMCN_PRIOR_INVGAMMA:  // -(a+1) log(y) - gammaln(a) - 1/y
-            if (y < 0.0) return ninf;
+        case MCMCN_PRIOR_INVGAMMA:  // -(a+1) log(y) - gammaln(a) - 1/y; open support in scipy: y == 0 -> -inf
+            if (y <= 0.0) return ninf;
             r = __dsub_rn(__dsub_rn(__dmul_rn(-__dadd_rn(pr.a, 1.0), log(y)), pr.c0), __ddiv_rn(1.0, y));
             break;
         case MCMCN_PRIOR_LAPLACE:  // log(0.5 * exp(-|y|)) (scipy has no _logpdf: log of the pdf)

@@ -197,6 +197,68 @@ def test_prior_mapping():
         priorFromScipy(scipy.stats.gamma(-1))
 
 
+def _devicePriorFormula(pr, x):
+    """The arithmetic of prior_logpdf (csrc/mcmcn_device.cuh) restated in numpy from the SAME record
+    the host hands to the device: checks that the constants priorFromScipy forms (c0, b, log_scale)
+    are the ones the device formulas need."""
+    inf = numpy.inf
+    y = numpy.float64((x - pr.loc) / pr.scale)
+    f = pr.family
+    with numpy.errstate(all="ignore"):
+        if f == nat.PRIOR_NORM:
+            return -y * y / 2.0 - 0.9189385332046727 - pr.log_scale
+        if f == nat.PRIOR_GAMMA:
+            r = -inf if y < 0 else ((pr.a - 1.0) * numpy.log(y) if pr.a != 1.0 else 0.0) - y - pr.c0
+        elif f == nat.PRIOR_UNIFORM:
+            r = 0.0 if 0.0 <= y <= 1.0 else -inf
+        elif f == nat.PRIOR_EXPON:
+            r = -y if y >= 0 else -inf
+        elif f == nat.PRIOR_HALFNORM:
+            r = -0.22579135264472741 - 0.5 * (y * y) if y >= 0 else -inf
+        elif f == nat.PRIOR_LOGNORM:
+            r = -inf if y <= 0 else -(numpy.log(y) ** 2) / pr.c0 - numpy.log(pr.a * y * 2.5066282746310002)
+        elif f == nat.PRIOR_CAUCHY:
+            ay = abs(y)
+            r = -1.1447298858494002 - (numpy.log1p(ay * ay) if ay < 1 else 2.0 * numpy.log(ay) + numpy.log1p((numpy.float64(1.0) / ay) ** 2))
+        elif f == nat.PRIOR_T:
+            r = pr.c0 - (pr.a + 1.0) / 2.0 * numpy.log1p(y * y / pr.a)
+        elif f == nat.PRIOR_BETA:
+            r = -inf if (y < 0 or y > 1) else ((pr.b - 1.0) * numpy.log1p(-y) if pr.b != 1.0 else 0.0) + \
+                ((pr.a - 1.0) * numpy.log(y) if pr.a != 1.0 else 0.0) - pr.c0
+        elif f == nat.PRIOR_INVGAMMA:
+            r = -inf if y <= 0 else -(pr.a + 1.0) * numpy.log(y) - pr.c0 - numpy.float64(1.0) / y
+        elif f == nat.PRIOR_LAPLACE:
+            r = numpy.log(0.5 * numpy.exp(-abs(y)))
+        elif f == nat.PRIOR_LOGISTIC:
+            t = -abs(y)
+            r = t - 2.0 * numpy.log1p(numpy.exp(t))
+        elif f == nat.PRIOR_CHI2:
+            h = pr.a / 2.0 - 1.0
+            r = -inf if y < 0 else (h * numpy.log(y) if h != 0.0 else 0.0) - y / 2.0 - pr.c0 - pr.b
+        else:
+            raise ValueError(f)
+        return r - pr.log_scale
+
+
+def test_prior_records_reproduce_scipy_logpdf():
+    from engine import priorFromScipy
+    frozen = [scipy.stats.norm(1, 3), scipy.stats.gamma(2.5, loc=-1, scale=2), scipy.stats.gamma(1.0), scipy.stats.uniform(-2, 4),
+              scipy.stats.expon(-6, 4), scipy.stats.halfnorm(0, 3), scipy.stats.lognorm(0.8, scale=2), scipy.stats.cauchy(0, 5),
+              scipy.stats.t(4, 1, 3), scipy.stats.beta(2, 3, loc=-30, scale=60), scipy.stats.beta(1, 1), scipy.stats.invgamma(3, scale=2),
+              scipy.stats.laplace(0, 4), scipy.stats.logistic(1, 3), scipy.stats.chi2(4), scipy.stats.chi2(2)]
+    xs = [-40.0, -7.5, -1.0, -0.3, 0.0, 0.2, 0.5, 0.99, 1.0, 2.0, 3.7, 25.0, 400.0]
+    for d in frozen:
+        pr = priorFromScipy(d)
+        for x in xs:
+            with numpy.errstate(all="ignore"):
+                want = float(d.logpdf(x))
+            got = float(_devicePriorFormula(pr, x))
+            if numpy.isfinite(want):
+                assert abs(got - want) <= 1e-12 * max(abs(want), 1.0), (d.dist.name, x, got, want)
+            else:
+                assert (numpy.isnan(got) and numpy.isnan(want)) or got == want, (d.dist.name, x, got, want)
+
+
 class _FakeEngine(object):
     """Host stand-in for Engine.pooledNll so that the start-up logic runs without a GPU."""
 
