@@ -204,6 +204,8 @@ def _devicePriorFormula(pr, x):
     inf = numpy.inf
     y = numpy.float64((x - pr.loc) / pr.scale)
     f = pr.family
+    if not (pr.scale > 0.0) or numpy.isnan(y):                    # the device function's first line
+        return numpy.nan
     with numpy.errstate(all="ignore"):
         if f == nat.PRIOR_NORM:
             return -y * y / 2.0 - 0.9189385332046727 - pr.log_scale
@@ -246,7 +248,7 @@ def test_prior_records_reproduce_scipy_logpdf():
               scipy.stats.expon(-6, 4), scipy.stats.halfnorm(0, 3), scipy.stats.lognorm(0.8, scale=2), scipy.stats.cauchy(0, 5),
               scipy.stats.t(4, 1, 3), scipy.stats.beta(2, 3, loc=-30, scale=60), scipy.stats.beta(1, 1), scipy.stats.invgamma(3, scale=2),
               scipy.stats.laplace(0, 4), scipy.stats.logistic(1, 3), scipy.stats.chi2(4), scipy.stats.chi2(2)]
-    xs = [-40.0, -7.5, -1.0, -0.3, 0.0, 0.2, 0.5, 0.99, 1.0, 2.0, 3.7, 25.0, 400.0]
+    xs = [-40.0, -30.0, -7.5, -6.0, -2.0, -1.0, -0.3, 0.0, 0.2, 0.5, 0.99, 1.0, 2.0, 3.7, 25.0, 30.0, 400.0, numpy.inf, -numpy.inf, numpy.nan]
     for d in frozen:
         pr = priorFromScipy(d)
         for x in xs:
