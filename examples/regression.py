@@ -24,19 +24,23 @@ numpy.random.seed(12345)
 
 
 def generateData(nGroups, nResponsesPerGroup):
-    """example/regression.py:16-50."""
-    n = nGroups * nResponsesPerGroup
-    x = numpy.hstack([numpy.tile([1], (n))[numpy.newaxis].T, numpy.random.normal(size=(n, 1))])
-    beta = numpy.hstack([
-        numpy.repeat(numpy.random.normal(loc=0, scale=1, size=nGroups),
-                     [nResponsesPerGroup] * nGroups)[numpy.newaxis].T,
-        numpy.repeat(numpy.random.normal(loc=100, scale=100, size=nGroups),
-                     [nResponsesPerGroup] * nGroups)[numpy.newaxis].T])
-    y = numpy.sum(x * beta, axis=1) + numpy.random.normal(size=n)
-    trueValueString = "\nTrue value:\n"
-    for i in range(beta.shape[1]):
-        trueValueString += "\tbeta%i: {mean: %.2f, sd: %.2f}\n" % (i, numpy.mean(beta[:, i]), numpy.std(beta[:, 1]))
-    return {"X": x, "y": y}, trueValueString
+    """Mock data of the reference's example (example/regression.py:16-50): a constant and one
+    standard-normal predictor, group intercepts ~ N(0, 1), group slopes ~ N(100, 100), unit noise.
+    The global numpy stream (seeded above) is consumed in the reference's order -- predictor,
+    intercepts, slopes, noise -- so the data are the same numbers."""
+    nObservations = nGroups * nResponsesPerGroup
+    predictor = numpy.random.normal(size=nObservations)
+    intercept = numpy.random.normal(0.0, 1.0, nGroups)
+    slope = numpy.random.normal(100.0, 100.0, nGroups)
+    noise = numpy.random.normal(size=nObservations)
+    member = numpy.arange(nObservations) // nResponsesPerGroup      # group of each observation
+    X = numpy.column_stack([numpy.ones(nObservations), predictor])
+    y = intercept[member] + slope[member] * predictor + noise
+    # the reference reports the slope's sd for both coefficients (example/regression.py:45); kept, it is only a printout
+    sdShown = numpy.std(slope[member])
+    lines = ["\tbeta%i: {mean: %.2f, sd: %.2f}\n" % (i, numpy.mean(b[member]), sdShown)
+             for i, b in enumerate((intercept, slope))]
+    return {"X": X, "y": y}, "\nTrue value:\n" + "".join(lines)
 
 
 def main(pooling):

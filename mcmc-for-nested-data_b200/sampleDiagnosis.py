@@ -296,96 +296,96 @@ class Diagnostic(object):
         self._compute()
         return self._hdi
 
-    # ---------------------------------------------------------------- tables (:263-329)
+    # ---------------------------------------------------------------- tables (:257-405)
+    # One column specification per table drives the structured array (what `.assessment` /
+    # `.summary` return, as in the reference) and the CSV text; both tables are derived lazily.
+    _ASSESSMENT_SPEC = (("parameter", "S40", "'%s'"), ("rhat", float, "%.3f"), ("converged", bool, "%s"),
+                        ("effective n", float, "%.3f"), ("enough n", bool, "%s"), ("median", float, "%.3f"),
+                        ("HDI lower", float, "%.3f"), ("HDI upper", float, "%.3f"))
+    _SUMMARY_SPEC = (("parameter", "S40", "'%s'"), ("rhat min", float, "%.3f"), ("rhat median", float, "%.3f"),
+                     ("rhat max", float, "%.3f"), ("proportion converged", float, "%.3f"))
+
+    @staticmethod
+    def _structured(spec, records):
+        return numpy.array(records, dtype=[(title, kind) for title, kind, _ in spec])
+
+    @staticmethod
+    def _csvText(spec, table, keep=None):
+        """Header line + one formatted line per record whose (decoded) name passes `keep`."""
+        pattern = ",".join(fmt for _, _, fmt in spec)
+        lines = [",".join(title for title, _, _ in spec)]
+        for record in table:
+            label = record["parameter"].decode("ascii")
+            if keep is None or keep(label):
+                lines.append(pattern % ((label,) + tuple(record)[1:]))
+        return "\n".join(lines) + "\n"
+
     @property
     def assessment(self):
+        """Per key: R-hat, converged (< 1.1), ESS, enough (> 10 m), median, HDI; sorted by name bytes (:263-289)."""
         if self._assessment is None:
-            self._assess()
+            self._compute()
+            enough = self._m * 10
+            records = []
+            for key in self._keys:
+                rhat, ess = self._rhat[key], self._effectiveN[key]
+                lower, upper = self._hdi[key]
+                records.append((key.encode(), rhat, rhat < 1.1, ess, ess > enough, self._median[key], lower, upper))
+            self._assessment = numpy.sort(self._structured(self._ASSESSMENT_SPEC, records), order="parameter")
         return self._assessment
 
     def _assess(self):
-        if self._assessment is not None:
-            return
-        self._compute()
-        a = numpy.array([(key.encode(), self._rhat[key], self._rhat[key] < 1.1,
-                          self._effectiveN[key], self._effectiveN[key] > self._m * 10,
-                          self._median[key], self._hdi[key][0], self._hdi[key][1])
-                         for key in self._keys],
-                        dtype=[("parameter", "S40"), ("rhat", float), ("converged", bool),
-                               ("effective n", float), ("enough n", bool), ("median", float),
-                               ("HDI lower", float), ("HDI upper", float)])
-        self._assessment = numpy.sort(a, order="parameter")
+        return self.assessment
 
     @property
     def summary(self):
+        """Per parameter name, over its per-group keys (those with a '['): min / median / max R-hat and the
+        share of converged keys (:297-329)."""
         if self._summary is None:
-            self._summarise()
+            perName = {}
+            for record in self.assessment:
+                label = record["parameter"].decode("ascii")
+                if "[" in label:
+                    bucket = perName.setdefault(label.split("[")[0], ([], []))
+                    bucket[0].append(record["rhat"])
+                    bucket[1].append(record["converged"])
+            records = [(name, min(r), numpy.median(r), max(r), numpy.mean(c))
+                       for name, (r, c) in sorted(perName.items())]
+            self._summary = self._structured(self._SUMMARY_SPEC, records)
         return self._summary
 
     def _summarise(self):
-        if self._summary is not None:
-            return
-        self._assess()
-        parameterNames = sorted(set(name.decode("ascii").split("[")[0]
-                                    for name in self._assessment["parameter"] if b"[" in name))
-        rhats = dict((name, []) for name in parameterNames)
-        converged = dict((name, []) for name in parameterNames)
-        for row in self._assessment:
-            if b"[" not in row[0]:
-                continue
-            name = row[0].decode("ascii").split("[")[0]
-            rhats[name].append(row[1])
-            converged[name].append(row[2])
-        self._summary = numpy.array([(name, min(rhats[name]), numpy.median(rhats[name]),
-                                      max(rhats[name]), numpy.mean(converged[name]))
-                                     for name in parameterNames],
-                                    dtype=[("parameter", "S40"), ("rhat min", float),
-                                           ("rhat median", float), ("rhat max", float),
-                                           ("proportion converged", float)])
+        return self.summary
 
     def print(self, csvfile, individualSummary, hyperOnly):
-        """:331-379"""
-        if individualSummary and self.completelyPooled:
-            raise ValueError("MCMC was completely pooled. There is no individual summary.")
-        if hyperOnly and not self.partiallyPooled:
-            raise ValueError("MCMC was not partially pooled. There is no hyper-parameter.")
-        if individualSummary and hyperOnly:
-            raise ValueError("Choose individualSummary or hyperOnly. Not both.")
-        if (csvfile is None) and hyperOnly:
-            print("MCMC convergence diagnostic for hyper-parameters.")
-        elif (csvfile is None) and individualSummary:
-            print("Summary of MCMC convergence diagnostic.")
-        elif csvfile is None:
-            print("MCMC convergence diagnostic.")
-        if not individualSummary:
-            out = self._getAssessmentString(hyperOnly)
-        else:
-            out = self._getSummaryString()
-        if csvfile is None:
-            _stdout_csv(out)
-        else:
+        """Write one of the three tables to `csvfile`, or to stdout under its banner when None (:331-379)."""
+        refusals = ((individualSummary and self.completelyPooled,
+                     "MCMC was completely pooled. There is no individual summary."),
+                    (hyperOnly and not self.partiallyPooled,
+                     "MCMC was not partially pooled. There is no hyper-parameter."),
+                    (individualSummary and hyperOnly, "Choose individualSummary or hyperOnly. Not both."))
+        for refused, why in refusals:
+            if refused:
+                raise ValueError(why)
+        text = self._getSummaryString() if individualSummary else self._getAssessmentString(hyperOnly)
+        if csvfile is not None:
             with open(csvfile, "w") as h:
-                h.write(out)
+                h.write(text)
+            return
+        banner = "MCMC convergence diagnostic."
+        if hyperOnly:
+            banner = "MCMC convergence diagnostic for hyper-parameters."
+        elif individualSummary:
+            banner = "Summary of MCMC convergence diagnostic."
+        print(banner)
+        _stdout_csv(text)
 
     def _getAssessmentString(self, hyperOnly):
-        self._assess()
-        out = ",".join([key for key in self._assessment.dtype.names])
-        out += "\n"
-        for row in self._assessment:
-            if hyperOnly and (b"_" not in row[0]):
-                continue
-            out += "'%s',%.3f,%s,%.3f,%s,%.3f,%.3f,%.3f\n" % \
-                   (row[0].decode("ascii"), row[1], row[2], row[3], row[4], row[5], row[6], row[7])
-        return out
+        keep = (lambda label: "_" in label) if hyperOnly else None       # hyper-parameters: <name>_mu, <name>_sigma2
+        return self._csvText(self._ASSESSMENT_SPEC, self.assessment, keep)
 
     def _getSummaryString(self):
-        self._summarise()
-        out = ",".join([key for key in self._summary.dtype.names])
-        out += "\n"
-        for row in self._summary:
-            out += "'%s',%.3f,%.3f,%.3f,%.3f\n" % \
-                   (row[0].decode("ascii"), row[1], row[2], row[3], row[4])
-        return out
+        return self._csvText(self._SUMMARY_SPEC, self.summary)
 
 
 class Summary(object):
@@ -453,18 +453,17 @@ def diagnoseSamples(outputDirectory, assessConvergence=True, printSummary=True, 
     if assessConvergence:
         print("- Convergence Diagnostic -")
         diagnostic = Diagnostic(sampleDirectory)
-        path = diagnosticDirectory + "/diagnosticAssessment.csv"
-        diagnostic.print(path, False, False)
-        if diagnostic.completelyPooled:
-            diagnostic.print(None, False, False)
-        if diagnostic.partiallyPooled:
-            path = diagnosticDirectory + "/diagnosticAssessmentHyperOnly.csv"
-            diagnostic.print(path, False, True)
-            diagnostic.print(None, False, True)
-        if not diagnostic.completelyPooled:
-            path = diagnosticDirectory + "/diagnosticAssessmentIndividual.csv"
-            diagnostic.print(path, True, False)
-            diagnostic.print(None, True, False)
+        pooled, hyper = diagnostic.completelyPooled, diagnostic.partiallyPooled
+        # (wanted, file, individualSummary, hyperOnly, echoed to stdout as well)
+        reports = ((True, "diagnosticAssessment.csv", False, False, pooled),
+                   (hyper, "diagnosticAssessmentHyperOnly.csv", False, True, True),
+                   (not pooled, "diagnosticAssessmentIndividual.csv", True, False, True))
+        for wanted, fileName, individual, hyperOnly, echo in reports:
+            if not wanted:
+                continue
+            diagnostic.print(diagnosticDirectory + "/" + fileName, individual, hyperOnly)
+            if echo:
+                diagnostic.print(None, individual, hyperOnly)
 
     if printSummary:
         summary = Summary(sampleDirectory)
@@ -474,4 +473,5 @@ def diagnoseSamples(outputDirectory, assessConvergence=True, printSummary=True, 
 
 
 def _stdout_csv(content):
-    print("\t" + content.replace(",", ", ").replace("\n", "\n\t"))
+    """Tab-indented, comma-spaced echo of a CSV text (:762-763)."""
+    print("\t" + "\n\t".join(line.replace(",", ", ") for line in content.split("\n")))
