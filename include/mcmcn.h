@@ -184,6 +184,10 @@ typedef struct mcmcn_run_args {
      * CUDA events on `stream`, and mcmcn_timing_collect() adds their durations to [0..2] (ms)
      * and the number of timed launches to [6..8].  The call itself stays asynchronous. */
     double* timing;
+    /* optional pointwise log-likelihood of every retained state (saveLogLikelihood,
+     * posteriorSampling.py:890-891, :907-909): device double [store_rows][N][S], written at the same row
+     * index as `store` (which must be given); NULL = off */
+    double* loglik_store;
 } mcmcn_run_args;
 
 int mcmcn_version(void);
@@ -225,6 +229,13 @@ int mcmcn_pointwise_loglik(const mcmcn_model* model, const mcmcn_state* state,
 
 /* ---- diagnostics (sampleDiagnosis.py:158-255, :419-427, :766-776) ----------
  * x is device double [n_keys][m][n]: key-major, then half-chain, then draw. */
+/* Half-chains of n_keys columns [k0, k0 + n_keys) of a sample store (device [rows][ncol][stride], chain
+ * fastest, store_dtype 32 or 64; rows 0 .. 2n-1 are used) into out, device double [n_keys][out_m][n]:
+ * half-chain out_j0 + 2c + h = rows h n .. h n + n - 1 of chain c < n_chains (sampleDiagnosis.py:118-156).
+ * Several stores (shards of the chains) fill one `out` through out_j0. */
+int mcmcn_diag_halfchains(const void* store, int32_t store_dtype, int32_t n, int64_t ncol, int64_t stride,
+                          int64_t k0, int64_t n_keys, int32_t n_chains, int32_t out_m, int32_t out_j0,
+                          double* out, void* stream);
 /* per half-chain mean and ddof=1 variance: out_mean, out_var device [n_keys][m] */
 int mcmcn_diag_moments(const double* x, int64_t n_keys, int32_t m, int32_t n,
                        double* out_mean, double* out_var, void* stream);
@@ -280,6 +291,21 @@ int mcmcn_user_objective_free(void* handle);
 /* Known-answer hook for tests: out[0..3] = Philox4x32-10(counter[0..3], key[0..1]) computed on
  * the device (all three are device pointers to uint32). */
 int mcmcn_debug_philox(const void* counter, const void* key, void* out);
+
+/* Distribution-test hook: n draws of one of the step path's own samplers, one Philox key per draw
+ * (key = draw index, `seed`), written to the device array `out`:
+ *   SWEEP_NORMALS   out[2n]: both Box-Muller branches behind two consecutive sweeps' proposals
+ *   SWEEP_UNIFORMS  out[2n]: the two accept-test uniforms of the same Philox call
+ *   HYPER_NORMAL    out[n]:  the standard normal behind the Gibbs mu draw (posteriorSampling.py:485-487)
+ *   UNIT_INVGAMMA   out[n]:  1 / Gamma(a, 1) (Marsaglia-Tsang), the unit-scale draw behind sigma2
+ *                            (posteriorSampling.py:489-498: scipy.stats.invgamma(a).rvs())
+ *   UNIFORM53       out[n]:  the 53-bit uniform of the gamma sampler's accept test */
+#define MCMCN_DRAW_SWEEP_NORMALS 0
+#define MCMCN_DRAW_SWEEP_UNIFORMS 1
+#define MCMCN_DRAW_HYPER_NORMAL 2
+#define MCMCN_DRAW_UNIT_INVGAMMA 3
+#define MCMCN_DRAW_UNIFORM53 4
+int mcmcn_debug_draws(int kind, int64_t n, uint64_t seed, double a, double* out, void* stream);
 
 #ifdef __cplusplus
 }

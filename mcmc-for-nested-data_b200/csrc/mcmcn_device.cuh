@@ -1404,13 +1404,13 @@ static __global__ void __launch_bounds__(1024) complete_decide_kernel(const Comp
 
 // ---------------------------------------------------------------- retained-sample write-back
 // One row of StepMethod.values (:648-654, :780-787): per name [mu, sigma2 (partial)], theta[0..G-1].
-// store[(row*ncol + col)*S + chain]; a warp writes 32 consecutive chains.
+// store[(row*ncol + col)*S + chain]; a warp writes 32 consecutive chains.  grid = (columns, chain blocks).
 template <typename TS>
 __global__ void snapshot_kernel(int P, int G, int partial, int n_chains, int S, const double* theta,
                                 const double* hyper, TS* store_row) {
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ch = blockIdx.y * blockDim.x + threadIdx.x;
     const int per = G + (partial ? 2 : 0);
-    const int col = blockIdx.y;
+    const int col = blockIdx.x;
     if (ch >= n_chains) return;
     const int p = col / per, j = col - p * per;
     double v;

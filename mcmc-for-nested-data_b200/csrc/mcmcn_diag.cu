@@ -163,11 +163,54 @@ __global__ void row_mean_kernel(const double* __restrict__ x, long long rows, lo
     if (lane == 0) out[row] = s / (double)len;
 }
 
+// Half-chains of a slab of columns straight out of a sample store ([rows][ncol][S], chain fastest,
+// FP32 or FP64): out[k][j0 + 2 c + h][i] = store[h n + i][k0 + k][c] as doubles (sampleDiagnosis.py:118-156:
+// every chain's rows split into first / second half); out holds out_m half-chains per column.  32 x 32 tiles through shared memory: reads are
+// coalesced along the chains, writes along the draws.  grid = (row tiles, chain tiles, columns).
+template <typename TS>
+__global__ void halfchains_kernel(const TS* __restrict__ store, int n, long long ncol, long long S, long long k0,
+                                  int n_chains, int out_m, int out_j0, double* __restrict__ out) {
+    __shared__ double tile[32][33];
+    const int k = blockIdx.z;
+    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int two_n = 2 * n;
+    for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        const int r = r0 + dy, c = c0 + threadIdx.x;
+        if (r < two_n && c < n_chains) tile[dy][threadIdx.x] = (double)store[((long long)r * ncol + k0 + k) * S + c];
+    }
+    __syncthreads();
+    for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        const int c = c0 + dy, r = r0 + threadIdx.x;
+        if (r < two_n && c < n_chains) {
+            const int h = r >= n ? 1 : 0, i = r - h * n;
+            out[((long long)k * out_m + out_j0 + 2 * c + h) * n + i] = tile[threadIdx.x][dy];
+        }
+    }
+}
+
 }  // namespace mcmcn
 
 using namespace mcmcn;
 
 extern "C" {
+
+int mcmcn_diag_halfchains(const void* store, int32_t store_dtype, int32_t n, int64_t ncol, int64_t stride, int64_t k0,
+                          int64_t n_keys, int32_t n_chains, int32_t out_m, int32_t out_j0, double* out, void* stream) {
+    if (!store || !out || n < 1 || n_keys < 1 || n_keys > 65535 || k0 < 0 || k0 + n_keys > ncol || n_chains < 1 || n_chains > stride ||
+        out_j0 < 0 || out_j0 + 2 * n_chains > out_m || (store_dtype != 32 && store_dtype != 64)) {
+        set_error("bad diag_halfchains args");
+        return MCMCN_ERR_INVALID;
+    }
+    const dim3 grid((unsigned)((2 * n + 31) / 32), (unsigned)((n_chains + 31) / 32), (unsigned)n_keys);
+    if (grid.y > 65535) { set_error("too many chains for one halfchains launch"); return MCMCN_ERR_UNSUPPORTED; }
+    const dim3 block(32, 8, 1);
+    if (store_dtype == 32)
+        halfchains_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)store, n, ncol, stride, k0, n_chains, out_m, out_j0, out);
+    else
+        halfchains_kernel<double><<<grid, block, 0, (cudaStream_t)stream>>>((const double*)store, n, ncol, stride, k0, n_chains, out_m, out_j0, out);
+    CK(cudaGetLastError());
+    return MCMCN_OK;
+}
 
 int mcmcn_diag_moments(const double* x, int64_t n_keys, int32_t m, int32_t n, double* out_mean, double* out_var,
                        void* stream) {

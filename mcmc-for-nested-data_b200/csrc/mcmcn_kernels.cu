@@ -194,6 +194,18 @@ static int set_smem_attr(const void* fn, size_t smem) {
     return MCMCN_OK;
 }
 
+// Pointwise log-likelihood of the current state into out[N][S] (StepMethod.logLikelihood, :656-659).
+static int launch_pointwise(const KernelSet* ks, const mcmcn_model* m, const mcmcn_state* s, double* out, cudaStream_t stream) {
+    SweepArgs a;
+    fill_args(a, ks, m, s);
+    // the kernel derives each group's first observation index itself: no scratch, no synchronisation
+    const dim3 grid((unsigned)m->n_groups, (unsigned)((s->n_chains + 127) / 128), 1);
+    const long long* obs_off = nullptr;
+    void* args[] = {&a, &obs_off, &out};
+    CK(cudaLaunchKernel((const void*)ks->pointwise, grid, dim3(128, 1, 1), args, 0, stream));
+    return MCMCN_OK;
+}
+
 // Complete pooling with the observations split into small groups (mcmcn_model.split): per sweep
 // propose -> eval over the small groups -> decide.  Same iteration bookkeeping as mcmcn_run.
 static int run_complete_split(const mcmcn_model* m, const mcmcn_state* s, const mcmcn_run_args* r, cudaStream_t stream) {
@@ -254,12 +266,18 @@ static int run_complete_split(const mcmcn_model* m, const mcmcn_state* s, const 
         }
         if (r->store && i >= r->burn && (i % r->thin) == 0) {
             if (row >= r->store_rows) { set_error("sample store overflow at row %lld", (long long)row); return MCMCN_ERR_INVALID; }
-            const dim3 sg((unsigned)((s->n_chains + 127) / 128), (unsigned)P, 1);
+            const dim3 sg((unsigned)P, (unsigned)((s->n_chains + 127) / 128), 1);
             if (r->timing) r->timing[5] += 1.0;
             if (r->store_dtype == 64)
                 snapshot_kernel<double><<<sg, 128, 0, stream>>>(P, 1, 0, s->n_chains, S, s->theta, s->hyper, (double*)r->store + (size_t)row * P * S);
             else
                 snapshot_kernel<float><<<sg, 128, 0, stream>>>(P, 1, 0, s->n_chains, S, s->theta, s->hyper, (float*)r->store + (size_t)row * P * S);
+            if (r->loglik_store) {
+                const KernelSet* mks = nullptr;
+                int prc = validate(m, s, &mks);
+                if (!prc) prc = launch_pointwise(mks, m, s, r->loglik_store + (size_t)row * (size_t)m->n_obs * S, stream);
+                if (prc) return prc;
+            }
             ++row;
         }
     }
@@ -288,6 +306,8 @@ int mcmcn_run(const mcmcn_model* m, const mcmcn_state* s, const mcmcn_run_args* 
     int rc = validate(m, s, &ks);
     if (rc) return rc;
     if (!r || r->n_iter < 0 || r->thin < 1 || r->tune_interval < 1) { set_error("bad run args"); return MCMCN_ERR_INVALID; }
+    if (r->loglik_store && !r->store) { set_error("loglik_store goes with store (same rows)"); return MCMCN_ERR_INVALID; }
+    if (r->tune_interval > 65535) { set_error("tune_interval %d: the accept / reject counters since the last tune are 16 bits each", r->tune_interval); return MCMCN_ERR_INVALID; }
     if ((r->tape_z == nullptr) != (r->tape_u == nullptr)) { set_error("tape_z and tape_u go together"); return MCMCN_ERR_INVALID; }
     const bool partial = m->pooling == MCMCN_POOL_PARTIAL;
     if (partial && !s->hyper) { set_error("partial pooling needs state.hyper"); return MCMCN_ERR_INVALID; }
@@ -388,8 +408,7 @@ int mcmcn_run(const mcmcn_model* m, const mcmcn_state* s, const mcmcn_run_args* 
 
         if (r->store && i >= r->burn && (i % r->thin) == 0) {
             if (row >= r->store_rows) { set_error("sample store overflow at row %lld", (long long)row); return MCMCN_ERR_INVALID; }
-            const dim3 sg((unsigned)((s->n_chains + 127) / 128), (unsigned)ncol, 1);
-            if (ncol > 65535) { set_error("more than 65535 columns per row not supported yet"); return MCMCN_ERR_UNSUPPORTED; }
+            const dim3 sg((unsigned)ncol, (unsigned)((s->n_chains + 127) / 128), 1);
             tic(2);
             if (r->store_dtype == 64)
                 snapshot_kernel<double><<<sg, 128, 0, stream>>>(m->n_params, m->n_groups, partial ? 1 : 0, s->n_chains, s->stride,
@@ -398,6 +417,10 @@ int mcmcn_run(const mcmcn_model* m, const mcmcn_state* s, const mcmcn_run_args* 
                 snapshot_kernel<float><<<sg, 128, 0, stream>>>(m->n_params, m->n_groups, partial ? 1 : 0, s->n_chains, s->stride,
                                                                s->theta, s->hyper, (float*)r->store + (size_t)row * ncol * S);
             toc();
+            if (r->loglik_store) {                                     // Sampler._printLogLikelihood, :890-891, :907-909
+                rc = launch_pointwise(ks, m, s, r->loglik_store + (size_t)row * (size_t)m->n_obs * S, stream);
+                if (rc) return rc;
+            }
             ++row;
         }
     }
@@ -451,14 +474,7 @@ int mcmcn_pointwise_loglik(const mcmcn_model* m, const mcmcn_state* s, double* o
     int rc = validate(m, s, &ks);
     if (rc) return rc;
     if (!out) { set_error("null output"); return MCMCN_ERR_INVALID; }
-    SweepArgs a;
-    fill_args(a, ks, m, s);
-    // the kernel derives each group's first observation index itself: no scratch, no synchronisation
-    const dim3 grid((unsigned)m->n_groups, (unsigned)((s->n_chains + 127) / 128), 1);
-    const long long* obs_off = nullptr;
-    void* args[] = {&a, &obs_off, &out};
-    CK(cudaLaunchKernel((const void*)ks->pointwise, grid, dim3(128, 1, 1), args, 0, (cudaStream_t)stream_));
-    return MCMCN_OK;
+    return launch_pointwise(ks, m, s, out, (cudaStream_t)stream_);
 }
 
 }  // extern "C"
@@ -469,6 +485,49 @@ __global__ void philox_kat_kernel(const unsigned* c, const unsigned* k, unsigned
     out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
 }  // namespace mcmcn
+
+namespace mcmcn {
+// The step path's own samplers, one draw (or pair) per thread: what the free-running kernels consume.
+__global__ void debug_draws_kernel(int kind, long long n, unsigned long long seed, double a, double* out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // chain id = i, iteration 7, name/group index 3: any fixed counter will do, the key carries i
+    const uint4 r = philox_draw(i, seed, 7, MCMCN_STREAM_SWEEP, 3u, 1u);
+    switch (kind) {
+        case MCMCN_DRAW_SWEEP_NORMALS: {          // both Box-Muller branches of the sweep draw: out[2i], out[2i+1]
+            float zc, zs;
+            normal_pair_from(r.x, r.y, zc, zs);
+            out[2 * i] = (double)zc;
+            out[2 * i + 1] = (double)zs;
+            break;
+        }
+        case MCMCN_DRAW_SWEEP_UNIFORMS:           // the two accept uniforms of the sweep draw
+            out[2 * i] = uniform_from32(r.z);
+            out[2 * i + 1] = uniform_from32(r.w);
+            break;
+        case MCMCN_DRAW_HYPER_NORMAL: {           // the mu draw of the Gibbs update
+            const uint4 h = philox_draw(i, seed, 7, MCMCN_STREAM_HYPER, 3u, 0u);
+            out[i] = normal_from(h.x, h.y);
+            break;
+        }
+        case MCMCN_DRAW_UNIT_INVGAMMA:            // the sigma2 draw of the Gibbs update, unit scale
+            out[i] = 1.0 / gamma_draw(a, i, seed, 7, 3u);
+            break;
+        case MCMCN_DRAW_UNIFORM53:
+            out[i] = uniform_from(r.x, r.y);
+            break;
+        default:
+            out[i] = __longlong_as_double(0x7ff8000000000000LL);
+    }
+}
+}  // namespace mcmcn
+
+extern "C" int mcmcn_debug_draws(int kind, int64_t n, uint64_t seed, double a, double* out, void* stream_) {
+    if (n < 1 || !out || kind < 0 || kind > MCMCN_DRAW_UNIFORM53) { set_error("bad debug_draws args"); return MCMCN_ERR_INVALID; }
+    debug_draws_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(kind, n, seed, a, out);
+    CK(cudaGetLastError());
+    return MCMCN_OK;
+}
 
 extern "C" int mcmcn_debug_philox(const void* counter, const void* key, void* out) {
     if (!counter || !key || !out) { set_error("null pointer"); return MCMCN_ERR_INVALID; }

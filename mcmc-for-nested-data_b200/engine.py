@@ -115,18 +115,136 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
-class SampleStore(object):
-    """Retained samples on the device: [rows][ncol][S], chain fastest (include/mcmcn.h)."""
+def retainedCount(lo, hi, burn, thin):
+    """Number of iterations i in [lo, hi) that Sampler._loop retains (i >= burn and i % thin == 0, :887)."""
+    first = -(-max(lo, burn) // thin) * thin
+    return 0 if first >= hi else (hi - 1 - first) // thin + 1
 
-    def __init__(self, engine, nRows, dtype=torch.float64):
+
+class SampleStore(object):
+    """Retained samples, device layout [rows][ncol][S] with the chain fastest (include/mcmcn.h), and
+    optionally the pointwise log-likelihood of the same rows, [rows][N][S] (saveLogLikelihood).
+
+    resident (``path=None``): every row stays on the device -- ``tensor`` is [nRows][ncol][S].  Tests,
+        bench.py and example-scale runs (the CSV writer) use this.
+    streamed (``path`` given): the device holds a ring of two chunks of ``chunkRows`` rows.  When the
+        chains have filled one chunk it is copied to pinned host memory on a side stream while they
+        fill the other, and then written into ``path``, a .npy file [nRows][ncol][nChains] opened with
+        numpy.lib.format.open_memmap.  Device and pinned memory are 2 x chunkBytes each whatever the
+        run length (posteriorSampling.py:898-909, :933-936 appends a CSV row per retained iteration;
+        this is the same stream of rows in binary).  ``Engine.run`` splits its iterations at chunk
+        boundaries; ``finish()`` drains the ring.
+    ``logLikSink(row0, block)`` receives the pointwise log-likelihood rows as host arrays
+    [rows][N][nChains] in row order (streamed or not, at ``finish()`` when resident).
+    """
+
+    def __init__(self, engine, nRows, dtype=torch.float64, path=None, logLikelihood=False, logLikSink=None,
+                 chunkBytes=512 << 20):
         self.engine = engine
         self.nRows = int(nRows)
         self.dtype = dtype
-        self.tensor = torch.zeros((self.nRows, engine.nCol, engine.S), dtype=dtype, device=engine.device)
         self.iterations = []
+        self.path = path
+        self.streamed = path is not None
+        self.logLikSink = logLikSink
+        dev, S = engine.device, engine.S
+        rowBytes = engine.nCol * S * (8 if dtype == torch.float64 else 4)
+        if logLikelihood:
+            rowBytes += engine.nObservations * S * 8
+        if self.streamed:
+            self.chunkRows = int(max(1, min(self.nRows, chunkBytes // max(rowBytes, 1))))
+            deviceRows = 2 * self.chunkRows
+        else:
+            self.chunkRows = self.nRows
+            deviceRows = self.nRows
+        self.tensor = torch.zeros((deviceRows, engine.nCol, S), dtype=dtype, device=dev)
+        self.logLik = torch.zeros((deviceRows, engine.nObservations, S), dtype=torch.float64, device=dev) \
+            if logLikelihood else None
+        self.deviceBytes = self.tensor.numel() * self.tensor.element_size() + \
+            (self.logLik.numel() * 8 if self.logLik is not None else 0)
+        if self.streamed:
+            self._chunk, self._fill, self._done = 0, 0, 0          # ring position; rows already handed to the sink
+            self._side = torch.cuda.Stream(dev)
+            self._pin = [torch.empty((self.chunkRows, engine.nCol, S), dtype=dtype).pin_memory() for _ in range(2)]
+            self._pinLL = [torch.empty((self.chunkRows, engine.nObservations, S), dtype=torch.float64).pin_memory()
+                           for _ in range(2)] if logLikelihood else None
+            self._copied = [None, None]
+            self._pending = []
+            npdt = numpy.float64 if dtype == torch.float64 else numpy.float32
+            self.sink = numpy.lib.format.open_memmap(path, mode="w+", dtype=npdt,
+                                                     shape=(self.nRows, engine.nCol, engine.nChains))
+
+    # ---- what Engine.run needs
+    def deviceRow(self):
+        """Row of ``tensor`` that the next retained iteration goes to, and the capacity limit for this call."""
+        if not self.streamed:
+            return len(self.iterations), self.nRows
+        return self._chunk * self.chunkRows + self._fill, (self._chunk + 1) * self.chunkRows
+
+    def room(self):
+        """Retained rows the current call may still produce."""
+        if not self.streamed:
+            return self.nRows - len(self.iterations)
+        return self.chunkRows - self._fill
+
+    def advance(self, iterations):
+        """``iterations``: the retained iterations the launches just enqueued will write."""
+        self.iterations += iterations
+        if not self.streamed:
+            return
+        self._fill += len(iterations)
+        if self._fill == self.chunkRows:
+            self._flushChunk()
+
+    # ---- streaming
+    def _flushChunk(self):
+        c, n = self._chunk, self._fill
+        if n == 0:
+            return
+        main = torch.cuda.current_stream(self.engine.device)
+        filled = torch.cuda.Event()
+        filled.record(main)
+        self._side.wait_event(filled)
+        r0 = c * self.chunkRows
+        with torch.cuda.stream(self._side):
+            self._pin[c][:n].copy_(self.tensor[r0:r0 + n], non_blocking=True)
+            if self.logLik is not None:
+                self._pinLL[c][:n].copy_(self.logLik[r0:r0 + n], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self._side)
+        self._copied[c] = done
+        self._pending.append((c, n, self._done))
+        self._done += n
+        self._chunk, self._fill = 1 - c, 0
+        while len(self._pending) > 1:            # the chunk before this one: its copy ran while this one filled
+            self._retire(self._pending.pop(0))
+        if self._copied[self._chunk] is not None:    # the chains may overwrite the other chunk once it has left the device
+            main.wait_event(self._copied[self._chunk])
+
+    def _retire(self, item):
+        c, n, row0 = item
+        self._copied[c].synchronize()
+        nC = self.engine.nChains
+        self.sink[row0:row0 + n] = self._pin[c][:n].numpy()[:, :, :nC]
+        if self.logLik is not None and self.logLikSink is not None:
+            self.logLikSink(row0, self._pinLL[c][:n].numpy()[:, :, :nC])
+
+    def finish(self):
+        """Drain the ring and close the file (streamed), or hand the log-likelihood rows over (resident)."""
+        if self.streamed:
+            self._flushChunk()
+            while self._pending:
+                self._retire(self._pending.pop(0))
+            self.sink.flush()
+        elif self.logLik is not None and self.logLikSink is not None:
+            n = len(self.iterations)
+            if n:
+                self.logLikSink(0, self.logLik[:n, :, :self.engine.nChains].cpu().numpy())
 
     def hostArray(self):
-        """[rows][ncol][nChains] numpy array."""
+        """[rows][ncol][nChains] numpy array (the file's memmap when streamed, after finish())."""
+        if self.streamed:
+            return self.sink[:len(self.iterations)]
         return self.tensor[:len(self.iterations), :, :self.engine.nChains].cpu().numpy()
 
 
@@ -410,7 +528,24 @@ class Engine(object):
     # ------------------------------------------------------------------ run loop
     def run(self, iter0, nIter, burn, thin, store=None, tape=None, trace=False,
             tuneInterval=100, useLpriorOverride=None, timing=None):
-        """Advance every chain by nIter iterations (Sampler._loop, :862-896)."""
+        """Advance every chain by nIter iterations (Sampler._loop, :862-896).  With a streamed store the
+        iterations are issued in pieces that end where a chunk of the store's ring is full."""
+        if store is None or store.room() >= retainedCount(iter0, iter0 + nIter, burn, thin) or tape is not None or trace:
+            return self._run(iter0, nIter, burn, thin, store, tape, trace, tuneInterval, useLpriorOverride, timing)
+        cur, end = int(iter0), int(iter0 + nIter)
+        while cur < end:
+            room = store.room()
+            if room <= 0:
+                raise RuntimeError("sample store is full (%d rows)" % store.nRows)
+            # last iteration of this piece = the room-th retained one from `cur` on (or the end of the call)
+            first = -(-max(cur, burn) // thin) * thin
+            stop = min(end, first + (room - 1) * thin + 1)
+            self._run(cur, stop - cur, burn, thin, store, None, False, tuneInterval, useLpriorOverride, timing)
+            useLpriorOverride = None
+            cur = stop
+        return None
+
+    def _run(self, iter0, nIter, burn, thin, store, tape, trace, tuneInterval, useLpriorOverride, timing):
         P, G, S = self.P, self.G, self.S
         a = nat.RunArgs()
         a.iter0, a.n_iter, a.burn, a.thin = int(iter0), int(nIter), int(burn), int(thin)
@@ -430,18 +565,21 @@ class Engine(object):
                   "accept": torch.zeros(shape, dtype=torch.uint8, device=self.device)}
             a.trace_ll, a.trace_lp, a.trace_diff = _ptr(tr["ll"]), _ptr(tr["lp"]), _ptr(tr["diff"])
             a.trace_accept = _ptr(tr["accept"])
+        kept = []
         if store is not None:
             a.store = _ptr(store.tensor)
             a.store_dtype = 64 if store.dtype == torch.float64 else 32
-            a.store_row0 = len(store.iterations)
-            a.store_rows = store.nRows
-            store.iterations += [i for i in range(iter0, iter0 + nIter) if i % thin == 0 and i >= burn]
+            a.store_row0, a.store_rows = store.deviceRow()
+            a.loglik_store = _ptr(store.logLik)
+            kept = [i for i in range(iter0, iter0 + nIter) if i % thin == 0 and i >= burn]
         if useLpriorOverride is None:
             useLpriorOverride = self.partial and self.lpriorStale and iter0 == 0
         a.use_lprior_override = 1 if useLpriorOverride else 0
         if timing is not None:      # numpy float64[12], see mcmcn_run_args.timing; read with collectTiming()
             a.timing = timing.ctypes.data_as(ctypes.c_void_p)
         nat.call("mcmcn_run", ctypes.byref(self.model), ctypes.byref(self.state), ctypes.byref(a), self.stream)
+        if store is not None:
+            store.advance(kept)
         if iter0 == 0 and nIter > 0:
             self.lpriorStale = False
         del keep

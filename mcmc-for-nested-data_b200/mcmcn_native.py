@@ -82,7 +82,7 @@ class RunArgs(ctypes.Structure):
                 ("store", c_void_p), ("store_dtype", ctypes.c_int32),
                 ("use_lprior_override", ctypes.c_int32),
                 ("store_row0", ctypes.c_int64), ("store_rows", ctypes.c_int64),
-                ("timing", c_void_p)]
+                ("timing", c_void_p), ("loglik_store", c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/mcmcn.h declares
@@ -100,6 +100,9 @@ PROTOTYPES = {
     "mcmcn_pooled_nll": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_void_p, c_void_p, c_void_p]),
     "mcmcn_pointwise_loglik": (ctypes.c_int, [ctypes.POINTER(Model), ctypes.POINTER(State),
                                               c_void_p, c_void_p]),
+    "mcmcn_diag_halfchains": (ctypes.c_int, [c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64,
+                                             ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                             c_void_p, c_void_p]),
     "mcmcn_diag_moments": (ctypes.c_int, [c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                           c_void_p, c_void_p, c_void_p]),
     "mcmcn_diag_variogram": (ctypes.c_int, [c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
@@ -120,7 +123,11 @@ PROTOTYPES = {
                                                     ctypes.POINTER(c_void_p)]),
     "mcmcn_user_objective_free": (ctypes.c_int, [c_void_p]),
     "mcmcn_debug_philox": (ctypes.c_int, [c_void_p, c_void_p, c_void_p]),
+    "mcmcn_debug_draws": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_double,
+                                         c_void_p, c_void_p]),
 }
+
+DRAW_SWEEP_NORMALS, DRAW_SWEEP_UNIFORMS, DRAW_HYPER_NORMAL, DRAW_UNIT_INVGAMMA, DRAW_UNIFORM53 = range(5)
 
 _lib = None
 

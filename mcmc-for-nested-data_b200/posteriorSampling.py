@@ -10,9 +10,9 @@ What changes on purpose (BASELINE.json north star):
   * proposals / accept uniforms come from per-chain Philox streams keyed by the global chain id
     (the reference uses numpy's global MT19937, seed = chain); start states still come from each
     chain's MT19937 stream in the reference's order, so they equal the reference's.
-  * at scale the retained samples go to a binary store (``sample/samples.npy`` +
-    ``sample/manifest.json``) that ``sampleDiagnosis`` reads; at example scale the reference's
-    ``sample.<chain>.csv`` / ``logLikelihood.<chain>.csv`` files are written.
+  * at scale the retained samples stream into a binary store (``sample/samples[.rank<r>].npy`` +
+    ``sample/manifest.json``, one shard file per rank) that ``sampleDiagnosis`` reads; at example scale
+    the reference's ``sample.<chain>.csv`` / ``logLikelihood.<chain>.csv`` files are written.
 Under ``torch.distributed`` (one process per GPU) the chains are split contiguously over the
 ranks; sampling needs no communication.
 """
@@ -33,6 +33,9 @@ from objectives import Objective
 CSV_VALUE_LIMIT = int(os.environ.get("MCMCN_CSV_LIMIT", 20000000))
 # the pointwise log-likelihood output is refused above this many values (rows x N x chains)
 LOGLIK_VALUE_LIMIT = int(os.environ.get("MCMCN_LOGLIK_LIMIT", 200000000))
+# the binary store keeps the chains' FP64 values; "float32" (6e-8 relative, below the reference's "%f"
+# for |values| < 16) is an explicit opt-in that the manifest records
+STORE_DTYPE = os.environ.get("MCMCN_STORE_DTYPE", "float64")
 
 
 def samplePosterior(nChains, nIter, nSamples,
@@ -47,6 +50,16 @@ def samplePosterior(nChains, nIter, nSamples,
     (see the reference's docstring, posteriorSampling.py:36-144, for the arguments)."""
     startTime = datetime.datetime.now()
     rank, world = _rankWorld()
+
+    # argument errors are raised identically on every rank, before the first collective
+    if not isinstance(logLikelihoodFunction, Objective):
+        raise TypeError("logLikelihoodFunction must be an objectives.Objective handle (a device function); "
+                        "Python callables cannot run on the GPU and there is no CPU fallback")
+    if pooling not in ("partial", "none", "complete"):             # :1040-1043
+        raise Exception("Invalid pooling: ", pooling)
+    burn, thin = burnThin(nIter, nSamples)                          # :1018-1027
+    if nChains < world:
+        raise ValueError("fewer chains (%d) than ranks (%d)" % (nChains, world))
 
     if rank == 0:
         if os.path.exists(outputDirectory):
@@ -65,89 +78,25 @@ def samplePosterior(nChains, nIter, nSamples,
     if displayProgress and rank == 0:
         print(msg)
 
-    if not isinstance(logLikelihoodFunction, Objective):
-        raise TypeError("logLikelihoodFunction must be an objectives.Objective handle (a device function); "
-                        "Python callables cannot run on the GPU and there is no CPU fallback")
-    if pooling not in ("partial", "none", "complete"):             # :1040-1043
-        raise Exception("Invalid pooling: ", pooling)
-    burn, thin = burnThin(nIter, nSamples)                          # :1018-1027
+    # a rank that fails between here and the closing barrier tells its peers, so that nobody waits forever
+    failure = None
+    try:
+        elapsed = _sampleShard(rank, world, nChains, nIter, burn, thin, parameterName, nGroups, nResponsesPerGroup,
+                               pooling, logLikelihoodFunction, sampleDirectory, logDirectory, saveLogLikelihood,
+                               priorDistribution, startWithMLE, startingPointValueRange, displayProgress,
+                               loggingLevel, logger)
+    except BaseException as err:        # noqa: B902 -- re-raised below, after the peers know
+        failure = err
+    if world > 1:
+        import torch.distributed as dist
+        flag = torch.tensor([0 if failure is None else 1], dtype=torch.int32,
+                            device="cuda" if dist.get_backend() == "nccl" else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if failure is None and int(flag[0]):
+            failure = RuntimeError("samplePosterior failed on another rank")
+    if failure is not None:
+        raise failure
 
-    # chains of this rank (contiguous global ids; Philox and the start-state RNG are keyed by them)
-    lo, hi = (nChains * rank) // world, (nChains * (rank + 1)) // world
-    myChains = hi - lo
-    if myChains < 1:
-        raise ValueError("fewer chains (%d) than ranks (%d)" % (nChains, world))
-
-    eng = Engine(logLikelihoodFunction, nGroups, nResponsesPerGroup, pooling, myChains,
-                 priorDistribution=priorDistribution, chainId0=lo,
-                 seed=int(os.environ.get("MCMCN_SEED", "0")))
-    chainLoggers = [_getLogger(logDirectory + "/mcmc.chain%.2i.log" % c, "mcmc.chain%.2i" % c, loggingLevel)
-                    for c in range(lo, hi)] if myChains <= 64 else []
-    if pooling == "partial" and priorDistribution is not None:
-        logger.info("Partial pooling ignores prior distribution.")  # :713-714
-    _progress(logger, displayProgress and rank == 0, "Started looking for a reasonable starting state.")
-    eng.initialise(parameterName, startingPointValueRange, startWithMLE, logger)
-    _progress(logger, displayProgress and rank == 0, "Found a reasonable starting state.")
-
-    retained = retainedIterations(nIter, burn, thin)
-    nValues = len(retained) * eng.nCol * nChains
-    useCsv = nValues <= CSV_VALUE_LIMIT
-    store = SampleStore(eng, max(len(retained), 1), torch.float64 if useCsv else torch.float32)
-    pointwise = []
-    if saveLogLikelihood:
-        if len(retained) * eng.nObservations * nChains > LOGLIK_VALUE_LIMIT:
-            raise ValueError("saveLogLikelihood=True would write %d x %d x %d log-likelihood values; pass "
-                             "saveLogLikelihood=False (or raise MCMCN_LOGLIK_LIMIT)"
-                             % (len(retained), eng.nObservations, nChains))
-
-    # ---- Sampler._loop (:862-896): segments end at progress marks and, when the pointwise
-    # log-likelihood is wanted, at every retained iteration
-    stops = set([nIter])
-    loggingInterval = int(numpy.round(nIter / 10.))
-    if loggingInterval > 0:
-        stops.update(range(loggingInterval, nIter, loggingInterval))
-    if saveLogLikelihood:
-        stops.update(i + 1 for i in retained)
-    loopStart = datetime.datetime.now()
-    _progress(logger, displayProgress and rank == 0, r"Sampling started. 0% complete.")
-    cur = 0
-    for stop in sorted(stops):
-        eng.run(cur, stop - cur, burn, thin, store=store)
-        cur = stop
-        if saveLogLikelihood and (stop - 1) in retained:
-            pointwise.append(eng.pointwiseLogLikelihood())          # [N][myChains]
-        if loggingInterval > 0 and stop % loggingInterval == 0 and stop < nIter:
-            torch.cuda.synchronize()
-            now = datetime.datetime.now()
-            percentage = float(stop) / nIter
-            remain = (1 - percentage) * (now - loopStart) / percentage
-            _progress(logger, displayProgress and rank == 0,
-                      "%i%% complete. ETA: %s." % (percentage * 100, _getStrfTime(now + remain)))
-    torch.cuda.synchronize()
-    elapsed = datetime.datetime.now() - loopStart
-    _progress(logger, displayProgress and rank == 0, "100%% complete. Elapsed Time: %s."
-              % datetime.timedelta(seconds=int(elapsed.total_seconds())))
-
-    # ---- outputs
-    rows = store.hostArray()                                        # [rows][ncol][myChains]
-    header = sampleHeader(parameterName, eng.G, pooling)
-    if useCsv:
-        for c in range(myChains):
-            writeSampleCsv(sampleDirectory + "/sample.%i.csv" % (lo + c), lo + c, header,
-                           retained, rows[:, :, c])
-    else:
-        _writeBinaryStore(sampleDirectory, rows, header, retained, lo, hi, rank, world, pooling)
-    if saveLogLikelihood:
-        for c in range(myChains):
-            with open(sampleDirectory + "/logLikelihood.%i.csv" % (lo + c), "w") as h:
-                for pw in pointwise:
-                    h.write(",".join(["%f" % v for v in pw[:, c]]))
-                    h.write("\n")
-    for c, lg in enumerate(chainLoggers):
-        lg.info("chain %i. 100%% complete. Elapsed Time: %s."
-                % (lo + c, datetime.timedelta(seconds=int(elapsed.total_seconds()))))
-
-    _barrier(world)
     endTime = datetime.datetime.now()
     msg = "Finished. The elapsed time in total is %s." \
         % datetime.timedelta(seconds=int((endTime - startTime).total_seconds()))
@@ -155,6 +104,99 @@ def samplePosterior(nChains, nIter, nSamples,
     if displayProgress and rank == 0:
         print("")
         _printProgress(msg)
+
+
+def _sampleShard(rank, world, nChains, nIter, burn, thin, parameterName, nGroups, nResponsesPerGroup, pooling,
+                 objective, sampleDirectory, logDirectory, saveLogLikelihood, priorDistribution, startWithMLE,
+                 startingPointValueRange, displayProgress, loggingLevel, logger):
+    """This rank's chains (contiguous global ids; Philox and the start-state streams are keyed by them):
+    start state, Sampler._loop (:862-896), sample files."""
+    lo, hi = (nChains * rank) // world, (nChains * (rank + 1)) // world
+    myChains = hi - lo
+    show = displayProgress and rank == 0
+
+    eng = Engine(objective, nGroups, nResponsesPerGroup, pooling, myChains,
+                 priorDistribution=priorDistribution, chainId0=lo,
+                 seed=int(os.environ.get("MCMCN_SEED", "0")))
+    chainLoggers = [_getLogger(logDirectory + "/mcmc.chain%.2i.log" % c, "mcmc.chain%.2i" % c, loggingLevel)
+                    for c in range(lo, hi)] if myChains <= 64 else []
+    if pooling == "partial" and priorDistribution is not None:
+        logger.info("Partial pooling ignores prior distribution.")  # :713-714
+    _progress(logger, show, "Started looking for a reasonable starting state.")
+    eng.initialise(parameterName, startingPointValueRange, startWithMLE, logger)
+    _progress(logger, show, "Found a reasonable starting state.")
+
+    retained = retainedIterations(nIter, burn, thin)
+    nValues = len(retained) * eng.nCol * nChains
+    useCsv = nValues <= CSV_VALUE_LIMIT
+    if saveLogLikelihood and len(retained) * eng.nObservations * nChains > LOGLIK_VALUE_LIMIT:
+        raise ValueError("saveLogLikelihood=True would write %d x %d x %d log-likelihood values; pass "
+                         "saveLogLikelihood=False (or raise MCMCN_LOGLIK_LIMIT)"
+                         % (len(retained), eng.nObservations, nChains))
+
+    def appendLogLikelihood(row0, block):                          # block [rows][N][myChains], in row order
+        for c in range(myChains):                                   # Sampler._printLogLikelihood, :907-909
+            with open(sampleDirectory + "/logLikelihood.%i.csv" % (lo + c), "a") as h:
+                for r in range(block.shape[0]):
+                    h.write(",".join(["%f" % v for v in block[r, :, c]]))
+                    h.write("\n")
+
+    # Example scale: every row stays on the device and the reference's CSV files are written at the end.
+    # At scale: the rows stream through a two-chunk ring on the device into a .npy file per rank.
+    storeDtype = torch.float64
+    if not useCsv and STORE_DTYPE == "float32":
+        storeDtype = torch.float32
+    shardFile = "samples.npy" if world == 1 else "samples.rank%d.npy" % rank
+    store = SampleStore(eng, max(len(retained), 1), storeDtype,
+                        path=None if useCsv else os.path.join(sampleDirectory, shardFile),
+                        logLikelihood=bool(saveLogLikelihood), logLikSink=appendLogLikelihood)
+
+    # ---- Sampler._loop (:862-896): one call per progress mark; the store splits it where a chunk is full
+    stops = set([nIter])
+    loggingInterval = int(numpy.round(nIter / 10.))
+    if loggingInterval > 0:
+        stops.update(range(loggingInterval, nIter, loggingInterval))
+    loopStart = datetime.datetime.now()
+    _progress(logger, show, r"Sampling started. 0% complete.")
+    cur = 0
+    for stop in sorted(stops):
+        eng.run(cur, stop - cur, burn, thin, store=store)
+        cur = stop
+        if loggingInterval > 0 and stop % loggingInterval == 0 and stop < nIter:
+            torch.cuda.synchronize()
+            now = datetime.datetime.now()
+            percentage = float(stop) / nIter
+            remain = (1 - percentage) * (now - loopStart) / percentage
+            _progress(logger, show, "%i%% complete. ETA: %s." % (percentage * 100, _getStrfTime(now + remain)))
+    torch.cuda.synchronize()
+    elapsed = datetime.datetime.now() - loopStart
+    _progress(logger, show, "100%% complete. Elapsed Time: %s."
+              % datetime.timedelta(seconds=int(elapsed.total_seconds())))
+
+    # ---- outputs
+    store.finish()
+    header = sampleHeader(parameterName, eng.G, pooling)
+    if useCsv:
+        rows = store.hostArray()                                    # [rows][ncol][myChains]
+        for c in range(myChains):
+            writeSampleCsv(sampleDirectory + "/sample.%i.csv" % (lo + c), lo + c, header,
+                           retained, rows[:, :, c])
+    for c, lg in enumerate(chainLoggers):
+        lg.info("chain %i. 100%% complete. Elapsed Time: %s."
+                % (lo + c, datetime.timedelta(seconds=int(elapsed.total_seconds()))))
+    global lastRun
+    lastRun = {"engine": eng, "store": store, "retained": retained, "chains": (lo, hi),
+               "sampling_seconds": elapsed.total_seconds(), "store_device_bytes": store.deviceBytes}
+    _barrier(world)                                                 # every shard file is complete
+    if not useCsv and rank == 0:
+        writeManifest(sampleDirectory, header, retained, nChains, world, pooling,
+                      "float64" if storeDtype == torch.float64 else "float32")
+    return elapsed
+
+
+# What the last samplePosterior call of this process left on the device (engine, store, timings): lets a
+# caller that holds the process (bench.py, notebooks) run convergenceFromStore without re-reading files.
+lastRun = None
 
 
 # ------------------------------------------------------------------------------ output format
@@ -179,22 +221,20 @@ def writeSampleCsv(path, chain, header, iterations, rows):
             h.write("\n")
 
 
-def _writeBinaryStore(sampleDirectory, rows, header, iterations, lo, hi, rank, world, pooling):
-    """samples.npy [rows][ncol][chains] (+ manifest.json); one file per rank when sharded."""
-    name = "samples.npy" if world == 1 else "samples.rank%d.npy" % rank
-    numpy.save(os.path.join(sampleDirectory, name), rows)
-    if world == 1:
-        man = {"file": name, "header": header, "iterations": list(map(int, iterations)),
-               "chains": list(range(lo, hi)), "pooling": pooling, "dtype": str(rows.dtype),
-               "layout": "[rows][columns][chains]"}
-        with open(os.path.join(sampleDirectory, "manifest.json"), "w") as h:
-            json.dump(man, h)
-    else:
-        man = {"file": name, "header": header, "iterations": list(map(int, iterations)),
-               "chains": list(range(lo, hi)), "pooling": pooling, "dtype": str(rows.dtype),
-               "layout": "[rows][columns][chains]", "rank": rank, "world": world}
-        with open(os.path.join(sampleDirectory, "manifest.rank%d.json" % rank), "w") as h:
-            json.dump(man, h)
+def writeManifest(sampleDirectory, header, iterations, nChains, world, pooling, dtype):
+    """``sample/manifest.json``: what sampleDiagnosis.openSamples reads.  One shard file per rank, each
+    [rows][columns][chains of that rank] (.npy), chains split contiguously over the ranks."""
+    shards = []
+    for r in range(world):
+        lo, hi = (nChains * r) // world, (nChains * (r + 1)) // world
+        shards.append({"file": "samples.npy" if world == 1 else "samples.rank%d.npy" % r, "chains": [lo, hi]})
+    man = {"format": "mcmcn-samples-2", "header": list(header), "iterations": list(map(int, iterations)),
+           "nChains": int(nChains), "pooling": pooling, "dtype": dtype,
+           "layout": "[rows][columns][chains]", "shards": shards}
+    if dtype == "float32":
+        man["note"] = "draws rounded to float32 on request (MCMCN_STORE_DTYPE=float32): 6e-8 relative"
+    with open(os.path.join(sampleDirectory, "manifest.json"), "w") as h:
+        json.dump(man, h)
 
 
 # ------------------------------------------------------------------------------ plumbing

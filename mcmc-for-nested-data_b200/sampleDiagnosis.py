@@ -65,22 +65,32 @@ def keyRange(nKeys, rank, world):
 
 def exchangeByKey(local, group):
     """Key-partitioned exchange for the pooled order statistics:
-    ``local`` is this rank's [n_keys][len] draws; rank r becomes the owner of keys keyRange(r)
-    and receives every rank's draws of those keys, concatenated in rank (= chain) order:
-    returns [keys_owned][world * len].  One all-to-all over NVLink with NCCL; backends without
-    all-to-all (gloo, used by the CPU tests) run the same exchange as one gather per owner."""
+    ``local`` is this rank's [n_keys][len_r] draws (len_r may differ between ranks); rank r becomes the
+    owner of keys keyRange(r) and receives every rank's draws of those keys, concatenated in rank
+    (= chain) order: returns [keys_owned][sum of len_r].  One all-to-all over NVLink with NCCL; backends
+    without all-to-all (gloo, used by the CPU tests) run the same exchange as one gather per owner."""
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     nKeys, length = local.shape
+    lens = [torch.zeros(1, dtype=torch.int64, device=local.device) for _ in range(world)]
+    dist.all_gather(lens, torch.tensor([length], dtype=torch.int64, device=local.device), group=group)
+    lens = [int(v) for v in lens]
     send = [local[slice(*keyRange(nKeys, r, world))].contiguous() for r in range(world)]
     lo, hi = keyRange(nKeys, rank, world)
-    recv = [torch.empty((hi - lo, length), dtype=local.dtype, device=local.device) for _ in range(world)]
+    recv = [torch.empty((hi - lo, lens[r]), dtype=local.dtype, device=local.device) for r in range(world)]
     if dist.get_backend(group) == "nccl":
         dist.all_to_all(recv, send, group=group)
     else:
+        most = max(lens)                                 # gather wants equal shapes: pad to the longest, trim after
         for r in range(world):
-            dist.gather(send[r], gather_list=recv if r == rank else None, dst=dist.get_global_rank(group, r) if group is not None else r,
+            klo, khi = keyRange(nKeys, r, world)
+            padded = torch.zeros((khi - klo, most), dtype=local.dtype, device=local.device)
+            padded[:, :length] = send[r]
+            got = [torch.empty_like(padded) for _ in range(world)] if r == rank else None
+            dist.gather(padded, gather_list=got, dst=dist.get_global_rank(group, r) if group is not None else r,
                         group=group)
+            if r == rank:
+                recv = [got[q][:, :lens[q]] for q in range(world)]
     return torch.cat(recv, dim=1).contiguous()
 
 
@@ -114,16 +124,97 @@ def computeHpdInterval(samples, hdi_p=95):
     return (res[0, 1], res[0, 2])
 
 
-def loadSamples(sampleDirectory):
-    """Returns (keys in column order, array [nChains][rows][nKeys] float64, chain ids).
-    Reads the binary store if its manifest is present, else every ``sample*.csv`` (:102, :132)."""
+# ------------------------------------------------------------------------------ where the draws come from
+SLAB_BYTES = int(os.environ.get("MCMCN_DIAG_SLAB_BYTES", 1 << 30))     # device bytes of half-chains per slab of keys
+
+
+def _rankWorld():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+class SampleSource(object):
+    """The retained draws as the diagnostics want them, without ever materialising more than a slab:
+    ``blocks`` is a list of (array [rows][ncol][chains_b], chain ids) in chain order -- numpy arrays,
+    numpy memmaps of the binary store's shard files, or device tensors ([rows][ncol][S]: the engine's
+    resident store).  ``halfChains(k0, k1)`` gives device double [k1-k0][2 chains][n] for a slab of
+    columns (mcmcn_diag_halfchains: every chain's rows split into first / second half, :118-156)."""
+
+    def __init__(self, keys, blocks, nRows):
+        self.keys = list(keys)
+        self.blocks = blocks                       # [(array-like [rows][ncol][>= chains], [chain ids])]
+        self.nRows = int(nRows)
+        self.chains = [c for _, ids in blocks for c in ids]
+        self.nChains = len(self.chains)
+
+    @classmethod
+    def fromArray(cls, samples, keys, chains=None):
+        """samples: [nChains][rows][nKeys] (what loadSamples returns / the CSV files hold)."""
+        samples = numpy.asarray(samples, dtype=numpy.float64)
+        nC, rows, _ = samples.shape
+        block = numpy.ascontiguousarray(numpy.transpose(samples, (1, 2, 0)))       # [rows][keys][chains]
+        return cls(keys, [(block, list(chains) if chains is not None else list(range(nC)))], rows)
+
+    def halfChains(self, k0, k1, dev):
+        n = self.nRows // 2
+        nk = k1 - k0
+        out = torch.empty((nk, 2 * self.nChains, n), dtype=torch.float64, device=dev)
+        st = _stream(dev)
+        j0 = 0
+        for arr, ids in self.blocks:
+            nC = len(ids)
+            if isinstance(arr, torch.Tensor):                   # resident store: gather straight from it
+                src, ncol, stride, kk = arr, arr.shape[1], arr.shape[2], k0
+            else:                                               # host rows: this slab of columns only
+                host = numpy.ascontiguousarray(arr[:2 * n, k0:k1, :nC])
+                src, ncol, stride, kk = torch.from_numpy(host).to(dev), nk, nC, 0
+            nat.call("mcmcn_diag_halfchains", _ptr(src), 64 if src.dtype == torch.float64 else 32, n, ncol, stride,
+                     kk, nk, nC, 2 * self.nChains, j0, _ptr(out), st)
+            j0 += 2 * nC
+            del src
+        return out
+
+    def columns(self, cols, r0, r1, dev):
+        """device double [chains][r1 - r0][len(cols)] (Summary: the groups of one name, rows r0..r1)."""
+        parts = []
+        for arr, ids in self.blocks:
+            nC = len(ids)
+            if isinstance(arr, torch.Tensor):
+                idx = torch.as_tensor(cols, device=arr.device)
+                blk = arr[r0:r1, :, :nC].index_select(1, idx)
+            else:
+                blk = torch.from_numpy(numpy.ascontiguousarray(arr[r0:r1][:, cols, :nC])).to(dev)
+            parts.append(blk.to(torch.float64).permute(2, 0, 1))
+        return torch.cat(parts, dim=0).contiguous()
+
+
+def openSamples(sampleDirectory, rank=0, world=1):
+    """SampleSource over what samplePosterior wrote: the binary store when ``manifest.json`` is there
+    (shard files are memory-mapped, never read whole), else every ``sample*.csv`` (:102, :132).
+    With world > 1 and one shard per rank, rank r opens its own shard only; ``sharded`` says so."""
     manifest = os.path.join(sampleDirectory, "manifest.json")
     if os.path.exists(manifest):
         with open(manifest) as h:
             man = json.load(h)
-        arr = numpy.load(os.path.join(sampleDirectory, man["file"]), mmap_mode="r")   # [rows][ncol][nChains]
-        data = numpy.ascontiguousarray(numpy.transpose(arr, (2, 0, 1)), dtype=numpy.float64)
-        return list(man["header"]), data, list(man["chains"])
+        shards = man.get("shards") or [{"file": man["file"], "chains": [man["chains"][0], man["chains"][-1] + 1]}]
+        sharded = world > 1 and len(shards) == world
+        mine = [shards[rank]] if sharded else shards
+        blocks = []
+        for sh in mine:
+            arr = numpy.load(os.path.join(sampleDirectory, sh["file"]), mmap_mode="r")    # [rows][ncol][chains]
+            blocks.append((arr, list(range(sh["chains"][0], sh["chains"][1]))))
+        src = SampleSource(man["header"], blocks, len(man["iterations"]))
+        src.sharded = sharded
+        return src
+    keys, data, chains = _loadCsv(sampleDirectory)
+    src = SampleSource.fromArray(data, keys, chains)
+    src.sharded = False
+    return src
+
+
+def _loadCsv(sampleDirectory):
     files = glob.glob(sampleDirectory + "/sample*.csv")
     if not files:
         raise FileNotFoundError("no sample*.csv under %s" % sampleDirectory)
@@ -142,13 +233,33 @@ def loadSamples(sampleDirectory):
     return keys, numpy.stack(frames), [chainOf(f) for f in files]
 
 
+def loadSamples(sampleDirectory):
+    """Returns (keys in column order, array [nChains][rows][nKeys] float64, chain ids) -- everything in
+    host memory; meant for example-scale runs and tests.  The diagnostics themselves go through
+    openSamples / SampleSource and never hold more than a slab."""
+    if os.path.exists(os.path.join(sampleDirectory, "manifest.json")):
+        src = openSamples(sampleDirectory)
+        data = numpy.concatenate([numpy.transpose(numpy.asarray(arr[:, :, :len(ids)], dtype=numpy.float64), (2, 0, 1))
+                                  for arr, ids in src.blocks], axis=0)
+        return src.keys, numpy.ascontiguousarray(data), src.chains
+    return _loadCsv(sampleDirectory)
+
+
 def gatherShards(t, group):
-    """all-gather a [n_keys][m_local][..] tensor along the half-chain axis (dim 1), rank order."""
+    """all-gather a [n_keys][m_local][..] tensor along the half-chain axis (dim 1), rank order; ranks may
+    hold different numbers of chains (padded to the largest for the collective, trimmed after)."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=t.device) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([t.shape[1]], dtype=torch.int64, device=t.device), group=group)
+    sizes = [int(v) for v in sizes]
+    most = max(sizes)
+    if t.shape[1] < most:
+        pad = torch.zeros((t.shape[0], most - t.shape[1]) + tuple(t.shape[2:]), dtype=t.dtype, device=t.device)
+        t = torch.cat([t, pad], dim=1)
     parts = [torch.empty_like(t) for _ in range(world)]
     dist.all_gather(parts, t.contiguous(), group=group)
-    return torch.cat(parts, dim=1).contiguous()
+    return torch.cat([p[:, :sz] for p, sz in zip(parts, sizes)], dim=1).contiguous()
 
 
 def mergeShards(mean, var, vario, group):
@@ -164,35 +275,63 @@ def mergeShards(mean, var, vario, group):
     return mean, var, total
 
 
-def convergenceFromStore(storeTensor, nRows, nChains, group=None):
+def _slabKeys(nKeys, mLocal, n):
+    """Keys per slab: SLAB_BYTES of FP64 half-chains, and within the segmented sort's 2^31 items."""
+    per = max(1, mLocal * n)
+    return int(max(1, min(nKeys, SLAB_BYTES // (8 * per), ((1 << 31) - 1) // per, 65535)))
+
+
+def _convergenceSlab(x, group):
+    """R-hat quadruple [nk][4], per-lag sums and ESS of one slab of half-chains x [nk][mLocal][n]."""
+    dev = x.device
+    nk, mL, n = x.shape
+    st = _stream(dev)
+    f64 = torch.float64
+    mean = torch.empty((nk, mL), dtype=f64, device=dev)
+    var = torch.empty((nk, mL), dtype=f64, device=dev)
+    nat.call("mcmcn_diag_moments", _ptr(x), nk, mL, n, _ptr(mean), _ptr(var), st)
+    vario = torch.empty((nk, n), dtype=f64, device=dev)
+    nat.call("mcmcn_diag_variogram", _ptr(x), nk, mL, n, _ptr(vario), st)
+    if group is not None:
+        mean, var, vario = mergeShards(mean, var, vario, group)
+    m = mean.shape[1]
+    rh = torch.empty((nk, 4), dtype=f64, device=dev)
+    nat.call("mcmcn_diag_rhat", _ptr(mean), _ptr(var), nk, m, n, _ptr(rh), st)
+    return rh, vario, m
+
+
+def convergenceFromStore(storeTensor, nRows, nChains, group=None, timing=None):
     """R-hat and effective sample size of every column of a device-resident sample store
     ([rows][ncol][S], chain fastest; engine.SampleStore) without leaving the GPU: the same
     kernels and formulas as Diagnostic (:158-255), the rows split into first / second half per
-    chain (:118-156).  With ``group`` every rank holds a shard of the chains and the half-chain
-    moments and per-lag sums are exchanged by one NCCL all-gather (mergeShards).
-    Returns (rhat[ncol], ess[ncol]) as device tensors."""
+    chain (:118-156), the columns processed in slabs (no transposed copy of the whole store).  With
+    ``group`` every rank holds a shard of the chains and the half-chain moments and per-lag sums
+    are exchanged by one NCCL all-gather per slab (mergeShards); ``timing`` (a dict) then
+    receives the bytes this rank gathered.  Returns (rhat[ncol], ess[ncol]) as device tensors."""
     n = int(nRows) // 2
     if n < 2:
         raise ValueError("need at least 4 retained rows per chain")
     ncol = storeTensor.shape[1]
     dev = storeTensor.device
-    x = storeTensor[:2 * n, :, :nChains].permute(1, 2, 0).to(torch.float64)        # [ncol][nC][2n]
-    x = x.reshape(ncol, 2 * nChains, n).contiguous()                               # half-chains: chain c -> 2c, 2c+1
-    st = _stream(dev)
-    mL = 2 * nChains
-    mean = torch.empty((ncol, mL), dtype=torch.float64, device=dev)
-    var = torch.empty((ncol, mL), dtype=torch.float64, device=dev)
-    nat.call("mcmcn_diag_moments", _ptr(x), ncol, mL, n, _ptr(mean), _ptr(var), st)
-    vario = torch.empty((ncol, n), dtype=torch.float64, device=dev)
-    nat.call("mcmcn_diag_variogram", _ptr(x), ncol, mL, n, _ptr(vario), st)
-    if group is not None:
-        mean, var, vario = mergeShards(mean, var, vario, group)
-    m = mean.shape[1]
-    rh = torch.empty((ncol, 4), dtype=torch.float64, device=dev)
-    nat.call("mcmcn_diag_rhat", _ptr(mean), _ptr(var), ncol, m, n, _ptr(rh), st)
+    src = SampleSource(["c%d" % k for k in range(ncol)], [(storeTensor, list(range(nChains)))], 2 * n)
+    rhat = torch.empty((ncol,), dtype=torch.float64, device=dev)
     ess = torch.empty((ncol,), dtype=torch.float64, device=dev)
-    nat.call("mcmcn_diag_ess", _ptr(vario), _ptr(rh), ncol, m, n, None, _ptr(ess), st)
-    return rh[:, 3].contiguous(), ess
+    step = _slabKeys(ncol, 2 * nChains, n)
+    gathered = 0
+    for k0 in range(0, ncol, step):
+        k1 = min(ncol, k0 + step)
+        x = src.halfChains(k0, k1, dev)
+        rh, vario, m = _convergenceSlab(x, group)
+        nat.call("mcmcn_diag_ess", _ptr(vario), _ptr(rh), k1 - k0, m, n, None, _ptr(ess[k0:k1]), _stream(dev))
+        rhat[k0:k1] = rh[:, 3]
+        if group is not None:                      # what mergeShards received: means + variances of all m half-chains, per-lag sums of every rank
+            import torch.distributed as dist
+            gathered += (k1 - k0) * (2 * m + n * dist.get_world_size(group)) * 8
+        del x
+    if timing is not None:
+        timing["gathered_bytes"] = gathered
+        timing["slabs"] = (ncol + step - 1) // step
+    return rhat, ess
 
 
 def chainRange(nChains, rank, world):
@@ -201,70 +340,76 @@ def chainRange(nChains, rank, world):
 
 
 class Diagnostic(object):
-    def __init__(self, sampleDirectory=None, samples=None, keys=None, group=None):
+    def __init__(self, sampleDirectory=None, samples=None, keys=None, group=None, source=None):
         """Diagnostic(sampleDirectory) as in the reference (:89-116).  Alternatively pass
-        ``samples`` = array [nChains][rows][nKeys] (+ ``keys``) already in memory.
+        ``samples`` = array [nChains][rows][nKeys] (+ ``keys``) already in memory, or a SampleSource.
         ``group``: a torch.distributed process group whose ranks each hold a shard of the
         chains; results are then over all ranks' chains."""
-        if samples is None:
-            keys, samples, _ = loadSamples(sampleDirectory)
-        samples = numpy.asarray(samples, dtype=numpy.float64)
-        self._keys = list(keys)
+        if source is None:
+            if samples is not None:
+                source = SampleSource.fromArray(samples, keys)
+            else:
+                rank, world = _rankWorld()
+                source = openSamples(sampleDirectory, rank, world)
+                if source.sharded and group is None:
+                    import torch.distributed as dist
+                    group = dist.group.WORLD
+        self._source = source
+        self._keys = list(source.keys)
         self._group = group
-        self._organiseSamples(samples)
+        self._organiseSamples()
         self._done = False
         self._hdiP = 95
         self._assessment = None
         self._summary = None
 
-    def _organiseSamples(self, samples):
-        """:118-156 -- split every chain's rows into first / second half."""
-        nChains, N, nKeys = samples.shape
+    def _organiseSamples(self):
+        """:118-156 -- every chain's rows are split into first / second half (done per slab on the device)."""
+        N = self._source.nRows
         n = N // 2
         if N != 2 * n:
             # the reference fails with a broadcast error on an odd row count (SURVEY Q10)
             raise ValueError("could not broadcast input array from shape (%d,) into shape (%d,)" % (N - n, n))
-        self._mLocal = 2 * nChains
+        self._mLocal = 2 * self._source.nChains
         self._n = n
         self.partiallyPooled = any("_" in k for k in self._keys)          # :143-144
         self.completelyPooled = not any("01]" in k for k in self._keys)   # :146-147
-        dev = _device()
-        # [nKeys][m][n]: key-major, half-chains (chain c -> rows 2c, 2c+1), draws contiguous
-        x = numpy.ascontiguousarray(numpy.transpose(samples.reshape(nChains, 2, n, nKeys), (3, 0, 1, 2)))
-        self._x = torch.from_numpy(x.reshape(nKeys, self._mLocal, n)).to(dev)
         self._m = self._mLocal
         if self._group is not None:
             import torch.distributed as dist
-            self._m = self._mLocal * dist.get_world_size(self._group)
+            t = torch.tensor([self._mLocal], dtype=torch.int64, device=_device())
+            dist.all_reduce(t, group=self._group)
+            self._m = int(t[0])
 
     # ---------------------------------------------------------------- device pipeline
     def _compute(self):
         if self._done:
             return
-        dev = self._x.device
-        nKeys, mL, n = self._x.shape
+        dev = _device()
+        nKeys, mL, n = len(self._keys), self._mLocal, self._n
         st = _stream(dev)
         f64 = torch.float64
-        mean = torch.empty((nKeys, mL), dtype=f64, device=dev)
-        var = torch.empty((nKeys, mL), dtype=f64, device=dev)
-        nat.call("mcmcn_diag_moments", _ptr(self._x), nKeys, mL, n, _ptr(mean), _ptr(var), st)
-        vario = torch.empty((nKeys, n), dtype=f64, device=dev)
-        nat.call("mcmcn_diag_variogram", _ptr(self._x), nKeys, mL, n, _ptr(vario), st)
-        if self._group is not None:
-            mean, var, vario = mergeShards(mean, var, vario, self._group)
-        m = mean.shape[1]
-        rh = torch.empty((nKeys, 4), dtype=f64, device=dev)
-        nat.call("mcmcn_diag_rhat", _ptr(mean), _ptr(var), nKeys, m, n, _ptr(rh), st)
-        ess = torch.empty((nKeys,), dtype=f64, device=dev)
-        rho = torch.empty((nKeys, n), dtype=f64, device=dev)
-        nat.call("mcmcn_diag_ess", _ptr(vario), _ptr(rh), nKeys, m, n, _ptr(rho), _ptr(ess), st)
-        pooled = self._x.reshape(nKeys, mL * n)
-        if self._group is not None:       # key-partitioned all-to-all: no rank holds every key's pooled draws
-            mh = pooledMedianHdi(pooled, self._hdiP, self._group).cpu().numpy()
-        else:
-            mh = _sortedMedianHdi(pooled.clone(), self._hdiP)
-        rh_h, ess_h = rh.cpu().numpy(), ess.cpu().numpy()
-        self._rhoArr = rho.cpu().numpy()
+        rh_h = numpy.empty((nKeys, 4))
+        ess_h = numpy.empty(nKeys)
+        mh = numpy.empty((nKeys, 3))
+        self._rhoArr = numpy.empty((nKeys, n))
+        step = _slabKeys(nKeys, mL, n)
+        for k0 in range(0, nKeys, step):
+            k1 = min(nKeys, k0 + step)
+            nk = k1 - k0
+            x = self._source.halfChains(k0, k1, dev)                   # [nk][mL][n]
+            rh, vario, m = _convergenceSlab(x, self._group)
+            ess = torch.empty((nk,), dtype=f64, device=dev)
+            rho = torch.empty((nk, n), dtype=f64, device=dev)
+            nat.call("mcmcn_diag_ess", _ptr(vario), _ptr(rh), nk, m, n, _ptr(rho), _ptr(ess), st)
+            pooled = x.reshape(nk, mL * n)                             # sorted in place: x is not needed again
+            if self._group is not None:   # key-partitioned all-to-all: no rank holds every key's pooled draws
+                mh[k0:k1] = pooledMedianHdi(pooled, self._hdiP, self._group).cpu().numpy()
+            else:
+                mh[k0:k1] = _sortedMedianHdi(pooled, self._hdiP)
+            rh_h[k0:k1], ess_h[k0:k1] = rh.cpu().numpy(), ess.cpu().numpy()
+            self._rhoArr[k0:k1] = rho.cpu().numpy()
+            del x, pooled
         k = self._keys
         self._B = dict(zip(k, rh_h[:, 0]))
         self._W = dict(zip(k, rh_h[:, 1]))
@@ -388,51 +533,74 @@ class Diagnostic(object):
         return self._csvText(self._SUMMARY_SPEC, self.summary)
 
 
-class Summary(object):
-    """Summarise individual parameter values (:430-491): per retained row the mean and the
-    median over groups of each parameter name, then mean / median / 95% HDI of those."""
+def gatherChains(v, group):
+    """all-gather per-(chain, row) values [chains_r][rows] along the chain axis, rank (= chain) order."""
+    return gatherShards(v.unsqueeze(0), group)[0]
 
-    def __init__(self, sampleDirectory=None, samples=None, keys=None):
-        if samples is None:
-            keys, samples, _ = loadSamples(sampleDirectory)
-        samples = numpy.asarray(samples, dtype=numpy.float64)      # [nChains][rows][nKeys]
-        self._n = samples.shape[1]
-        names = numpy.unique([name.split("[")[0] for name in keys if "[" in name])
+
+class Summary(object):
+    """Summarise individual parameter values (:430-491): per (chain, retained row) the mean and the
+    median over groups of each parameter name, then mean / median / 95% HDI of those over all chains
+    and rows.  The first step is local to a chain, so under ``group`` (chains sharded over ranks) every
+    rank reduces its own chains, the per-(chain, row) values are all-gathered in chain order and the
+    second step runs on the full vector: the result equals the single-process one bit for bit."""
+
+    def __init__(self, sampleDirectory=None, samples=None, keys=None, group=None, source=None):
+        if source is None:
+            if samples is not None:
+                source = SampleSource.fromArray(samples, keys)
+            else:
+                rank, world = _rankWorld()
+                source = openSamples(sampleDirectory, rank, world)
+                if source.sharded and group is None:
+                    import torch.distributed as dist
+                    group = dist.group.WORLD
+        keys = source.keys
+        self._n = source.nRows
+        names = sorted(set(name.split("[")[0] for name in keys if "[" in name))
         dev = _device()
         st = _stream(dev)
-        self._rows = {}
-        for s in ("groupMean", "groupMedian"):
-            self._rows[s] = {}
+        nC, nRows = source.nChains, source.nRows
+        self._rows = {"groupMean": {}, "groupMedian": {}}
         for name in names:
             cols = [i for i, key in enumerate(keys) if (name + "[") in key]      # substring match, :466-467
-            x = torch.from_numpy(numpy.ascontiguousarray(samples[:, :, cols])).to(dev)   # [chains][rows][G]
-            rows = x.shape[0] * x.shape[1]
             G = len(cols)
-            flat = x.reshape(rows, G).contiguous()
-            mean = torch.empty((rows,), dtype=torch.float64, device=dev)
-            nat.call("mcmcn_diag_row_mean", _ptr(flat), rows, G, _ptr(mean), st)
-            if G >= 2:
-                srt = flat.clone()
-                nat.call("mcmcn_diag_sort_keys", _ptr(srt), rows, G, st)
-                mh3 = torch.empty((rows, 3), dtype=torch.float64, device=dev)
-                nat.call("mcmcn_diag_median_hdi", _ptr(srt), rows, G, 1, _ptr(mh3), st)
-                med = mh3[:, 0]
-            else:
-                med = flat[:, 0]
-            for s, v in (("groupMean", mean), ("groupMedian", med)):
-                v = v.contiguous()
+            mean = torch.empty((nC, nRows), dtype=torch.float64, device=dev)
+            med = torch.empty((nC, nRows), dtype=torch.float64, device=dev)
+            # rows in slabs: at most SLAB_BYTES of [chains][rows][G] doubles on the device (and within
+            # the segmented sort's 2^31 items)
+            step = int(max(1, min(nRows, SLAB_BYTES // max(8 * nC * G, 1), ((1 << 31) - 1) // max(nC * G, 1))))
+            for r0 in range(0, nRows, step):
+                r1 = min(nRows, r0 + step)
+                x = source.columns(cols, r0, r1, dev)                               # [chains][r1-r0][G]
+                flat = x.reshape(nC * (r1 - r0), G)
+                part = torch.empty((nC * (r1 - r0),), dtype=torch.float64, device=dev)
+                nat.call("mcmcn_diag_row_mean", _ptr(flat), flat.shape[0], G, _ptr(part), st)
+                mean[:, r0:r1] = part.reshape(nC, r1 - r0)
+                if G >= 2:
+                    nat.call("mcmcn_diag_sort_keys", _ptr(flat), flat.shape[0], G, st)   # in place: flat is a scratch copy
+                    mh3 = torch.empty((flat.shape[0], 3), dtype=torch.float64, device=dev)
+                    nat.call("mcmcn_diag_median_hdi", _ptr(flat), flat.shape[0], G, 1, _ptr(mh3), st)
+                    med[:, r0:r1] = mh3[:, 0].reshape(nC, r1 - r0)
+                else:
+                    med[:, r0:r1] = x[:, :, 0]
+                del x, flat
+            for stat, v in (("groupMean", mean), ("groupMedian", med)):
+                if group is not None:
+                    v = gatherChains(v, group)
+                v = v.reshape(1, -1).contiguous()                                   # chain-major, like the reference's loop
                 avg = torch.empty((1,), dtype=torch.float64, device=dev)
-                nat.call("mcmcn_diag_row_mean", _ptr(v), 1, rows, _ptr(avg), st)
-                mh = _sortedMedianHdi(v.reshape(1, rows).clone(), 95.)
-                self._rows[s][str(name)] = (float(avg.cpu()[0]), mh[0, 0], mh[0, 1], mh[0, 2])
+                nat.call("mcmcn_diag_row_mean", _ptr(v), 1, v.shape[1], _ptr(avg), st)
+                mh = _sortedMedianHdi(v.clone(), 95.)
+                self._rows[stat][name] = (float(avg.cpu()[0]), mh[0, 0], mh[0, 1], mh[0, 2])
         self._summarise()
 
     def _summarise(self):
-        self._summary = "stats,parameter,mean,median,HDI lower,HDI upper\n"
-        for s in ("groupMean", "groupMedian"):
-            for name in sorted(self._rows[s]):
-                mean, median, lo, hi = self._rows[s][name]
-                self._summary += "%s,%s,%.4f,%.4f,%.4f,%.4f\n" % (s, name, mean, median, lo, hi)
+        lines = ["stats,parameter,mean,median,HDI lower,HDI upper"]
+        for stat in ("groupMean", "groupMedian"):
+            for name in sorted(self._rows[stat]):
+                lines.append("%s,%s,%.4f,%.4f,%.4f,%.4f" % ((stat, name) + self._rows[stat][name]))
+        self._summary = "\n".join(lines) + "\n"
 
     def print(self, csvfile):
         if csvfile is None:
@@ -445,21 +613,28 @@ class Summary(object):
 
 def diagnoseSamples(outputDirectory, assessConvergence=True, printSummary=True, nFigures=10):
     """Diagnose samples (sampleDiagnosis.py:11-85).  Same files and stdout as the reference;
-    ``nFigures`` is accepted for compatibility but figures are not produced."""
+    ``nFigures`` is accepted for compatibility but figures are not produced.  Under torch.distributed
+    with the binary store sharded one file per rank, every rank reduces its own chains (Diagnostic /
+    Summary exchange what they must) and rank 0 alone writes and prints."""
     sampleDirectory = outputDirectory + "/sample/"
     diagnosticDirectory = outputDirectory + "/diagnostic/"
-    os.makedirs(diagnosticDirectory, exist_ok=True)
+    rank, world = _rankWorld()
+    speaks = rank == 0
+    if speaks:
+        os.makedirs(diagnosticDirectory, exist_ok=True)
 
     if assessConvergence:
-        print("- Convergence Diagnostic -")
+        if speaks:
+            print("- Convergence Diagnostic -")
         diagnostic = Diagnostic(sampleDirectory)
+        diagnostic.assessment                                  # every rank takes part in the exchanges
         pooled, hyper = diagnostic.completelyPooled, diagnostic.partiallyPooled
         # (wanted, file, individualSummary, hyperOnly, echoed to stdout as well)
         reports = ((True, "diagnosticAssessment.csv", False, False, pooled),
                    (hyper, "diagnosticAssessmentHyperOnly.csv", False, True, True),
                    (not pooled, "diagnosticAssessmentIndividual.csv", True, False, True))
         for wanted, fileName, individual, hyperOnly, echo in reports:
-            if not wanted:
+            if not (wanted and speaks):
                 continue
             diagnostic.print(diagnosticDirectory + "/" + fileName, individual, hyperOnly)
             if echo:
@@ -467,8 +642,9 @@ def diagnoseSamples(outputDirectory, assessConvergence=True, printSummary=True, 
 
     if printSummary:
         summary = Summary(sampleDirectory)
-        summary.print(sampleDirectory + "/summary.csv")
-        summary.print(None)
+        if speaks:
+            summary.print(sampleDirectory + "/summary.csv")
+            summary.print(None)
     # figures (Figure, :494-759) are out of scope for the GPU engine
 
 

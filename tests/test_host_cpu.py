@@ -4,6 +4,7 @@ data packing, prior mapping, batched Nelder-Mead, start-state search, shard merg
 gloo with world_size 2) behaves like the reference / oracle.  No kernel is launched here."""
 
 import ctypes
+import json
 import os
 import re
 import subprocess
@@ -319,8 +320,8 @@ def _gloo_worker(rank, world, port, tmp):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     rs = numpy.random.RandomState(11)
-    x = rs.normal(size=(5, 12, 40))                       # [keys][m][n], all chains
-    lo, hi = sd.chainRange(6, rank, world)                # 6 chains = 12 half-chains
+    x = rs.normal(size=(5, 14, 40))                       # [keys][m][n], all chains
+    lo, hi = sd.chainRange(7, rank, world)                # 7 chains = 14 half-chains: 3 on rank 0, 4 on rank 1 (ragged)
     mine = x[:, 2 * lo:2 * hi, :]
     mean = torch.from_numpy(mine.mean(axis=2))
     var = torch.from_numpy(mine.var(axis=2, ddof=1))
@@ -333,6 +334,9 @@ def _gloo_worker(rank, world, port, tmp):
     pooled = torch.from_numpy(numpy.ascontiguousarray(mine.reshape(5, -1)))
     owned = sd.exchangeByKey(pooled, dist.group.WORLD)
     numpy.save(os.path.join(tmp, "owned.%d.npy" % rank), owned.numpy())
+    # Summary's exchange: per-(chain, row) values gathered along the chain axis, chain order
+    perChain = torch.from_numpy(numpy.ascontiguousarray(x[0, 2 * lo:2 * hi:2, :]))       # [chains of this rank][40]
+    numpy.save(os.path.join(tmp, "chains.%d.npy" % rank), sd.gatherChains(perChain, dist.group.WORLD).numpy())
     dist.destroy_process_group()
 
 
@@ -346,17 +350,18 @@ def test_shard_merge_over_gloo_world_size_2(tmp_path):
     b = numpy.load(tmp_path / "merged.1.npy")
     assert numpy.array_equal(a, b)                        # bit-identical on every rank
     rs = numpy.random.RandomState(11)
-    x = rs.normal(size=(5, 12, 40))
+    x = rs.normal(size=(5, 14, 40))
     mean, var = x.mean(axis=2), x.var(axis=2, ddof=1)
     vario = numpy.stack([[((x[k, :, t:] - x[k, :, :40 - t]) ** 2).sum() for t in range(40)] for k in range(5)])
-    numpy.testing.assert_array_equal(a[:60], mean.ravel())
-    numpy.testing.assert_array_equal(a[60:120], var.ravel())
-    numpy.testing.assert_allclose(a[120:], vario.ravel(), rtol=1e-13)
+    numpy.testing.assert_array_equal(a[:70], mean.ravel())
+    numpy.testing.assert_array_equal(a[70:140], var.ravel())
+    numpy.testing.assert_allclose(a[140:], vario.ravel(), rtol=1e-13)
     # exchangeByKey: rank r owns keys keyRange(5, r, 2) and holds ALL chains' draws of them, chain order
     import sampleDiagnosis as sd
     for r in range(2):
         lo, hi = sd.keyRange(5, r, 2)
         numpy.testing.assert_array_equal(numpy.load(tmp_path / ("owned.%d.npy" % r)), x[lo:hi].reshape(hi - lo, -1))
+        numpy.testing.assert_array_equal(numpy.load(tmp_path / ("chains.%d.npy" % r)), x[0, 0::2, :])
 
 
 def test_chain_ranges_partition_the_chains():
@@ -367,3 +372,80 @@ def test_chain_ranges_partition_the_chains():
             lo, hi = sd.chainRange(n, r, w)
             cover += list(range(lo, hi))
         assert cover == list(range(n))
+
+
+def test_retained_count_matches_the_loop_condition():
+    """engine.retainedCount = number of i in [lo, hi) with i >= burn and i % thin == 0 (posteriorSampling.py:887)."""
+    from engine import retainedCount
+    rs = numpy.random.RandomState(0)
+    for _ in range(300):
+        lo, n, burn, thin = int(rs.randint(0, 50)), int(rs.randint(0, 60)), int(rs.randint(0, 70)), int(rs.randint(1, 9))
+        want = len([i for i in range(lo, lo + n) if i >= burn and i % thin == 0])
+        assert retainedCount(lo, lo + n, burn, thin) == want
+
+
+def test_manifest_lists_the_shards_and_samples_load_in_chain_order(tmp_path):
+    """The sharded binary store (one .npy per rank + one manifest.json) as the diagnostics open it:
+    shard files are memory-mapped, chains come back in global order; a single-file store and the
+    round-1 manifest layout still load."""
+    import posteriorSampling as ps
+    import sampleDiagnosis as sd
+    rs = numpy.random.RandomState(5)
+    rows, ncol, nChains, world = 6, 4, 7, 3
+    full = rs.normal(size=(rows, ncol, nChains))
+    d = str(tmp_path) + "/"
+    header = ["a_mu", "a_sigma2", "a[000]", "a[001]"]
+    for r in range(world):
+        lo, hi = sd.chainRange(nChains, r, world)
+        numpy.save(d + "samples.rank%d.npy" % r, full[:, :, lo:hi])
+    ps.writeManifest(d, header, list(range(10, 22, 2)), nChains, world, "partial", "float64")
+    keys, data, chains = sd.loadSamples(d)
+    assert keys == header and chains == list(range(nChains))
+    numpy.testing.assert_array_equal(data, numpy.transpose(full, (2, 0, 1)))
+    for r in range(world):                                    # one shard per rank under torch.distributed
+        src = sd.openSamples(d, rank=r, world=world)
+        assert src.sharded and src.chains == list(range(*sd.chainRange(nChains, r, world))) and src.nRows == rows
+        assert isinstance(src.blocks[0][0], numpy.memmap)
+    assert not sd.openSamples(d, rank=0, world=2).sharded     # shard count != world: everybody reads everything
+    # single file, and the manifest the first store version wrote
+    one = str(tmp_path / "one") + "/"
+    os.makedirs(one)
+    numpy.save(one + "samples.npy", full)
+    ps.writeManifest(one, header, list(range(6)), nChains, 1, "partial", "float64")
+    numpy.testing.assert_array_equal(sd.loadSamples(one)[1], numpy.transpose(full, (2, 0, 1)))
+    with open(one + "manifest.json", "w") as h:
+        json.dump({"file": "samples.npy", "header": header, "iterations": list(range(6)),
+                   "chains": list(range(nChains)), "pooling": "partial", "dtype": "float64"}, h)
+    assert sd.loadSamples(one)[2] == list(range(nChains))
+
+
+def test_diagnostic_tables_and_stdout_text_from_given_statistics(capsys):
+    """Diagnostic's table / CSV / stdout code on the reference's own numbers (no device needed): the
+    per-key statistics are taken from the oracle, the text must equal the reference's files."""
+    import sampleDiagnosis as sd
+    from oracle.diagnosis_oracle import DiagnosticOracle
+    for case in ("reg_partial", "reg_none", "reg_complete"):
+        d = os.path.join(GOLDEN, case)
+        o = DiagnosticOracle(d)
+        o._compute()
+        diag = object.__new__(sd.Diagnostic)
+        diag._keys, diag._m = list(o.keys), o._m
+        diag._rhat, diag._effectiveN, diag._median, diag._hdi = o.rhat, o.effectiveN, o.median, o.hdi
+        diag._assessment = diag._summary = None
+        diag._done = True
+        diag.partiallyPooled, diag.completelyPooled = o.partiallyPooled, o.completelyPooled
+        assert diag._getAssessmentString(False) == open(d + "/diagnosticAssessment.csv").read()
+        if diag.partiallyPooled:
+            assert diag._getAssessmentString(True) == open(d + "/diagnosticAssessmentHyperOnly.csv").read()
+        if not diag.completelyPooled:
+            assert diag._getSummaryString() == open(d + "/diagnosticAssessmentIndividual.csv").read()
+        capsys.readouterr()
+        if diag.completelyPooled:
+            diag.print(None, False, False)
+        if diag.partiallyPooled:
+            diag.print(None, False, True)
+        if not diag.completelyPooled:
+            diag.print(None, True, False)
+        assert capsys.readouterr().out in open(d + "/diagnose.stdout.txt").read()
+        with pytest.raises(ValueError, match="Not both|no individual|no hyper"):
+            diag.print(None, True, True)

@@ -9,7 +9,14 @@
    chain id, so results do not depend on the GPU count).
 2. Diagnostic over the sharded chains (all-gather of per-half-chain summaries over NCCL; pooled
    median / HDI through a key-partitioned all-to-all) equals Diagnostic over all chains in one process.
+3. The same run forced into the binary store writes one shard file per rank plus one manifest;
+   diagnoseSamples under the process group (every rank opens its own shard; all-gather / all-to-all
+   for the between-chain statistics, pooled order statistics and Summary; rank 0 writes) produces the
+   same files and stdout as a single process reading all shards.
 Prints MULTI_GPU_OK on rank 0."""
+import contextlib
+import io
+import shutil
 import os
 import sys
 
@@ -43,9 +50,30 @@ def main():
     mine = allSamples[lo:hi]
     dShard = sd.Diagnostic(samples=mine, keys=keys, group=dist.group.WORLD)
     rhat, ess, med, hdi = dShard.rhat, dShard.effectiveN, dShard.median, dShard.hdi
+    # 3. sharded binary store
+    ps.CSV_VALUE_LIMIT = 0
+    ps.samplePosterior(nChains, nIter, nSamples, names, 24, nResp, "partial", handle, out + "/multibin",
+                       saveLogLikelihood=False, startingPointValueRange=ranges, displayProgress=False)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        sd.diagnoseSamples(out + "/multibin", nFigures=0)
+    shardedStdout = buf.getvalue()
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
+        files = ("diagnostic/diagnosticAssessment.csv", "diagnostic/diagnosticAssessmentHyperOnly.csv",
+                 "diagnostic/diagnosticAssessmentIndividual.csv", "sample/summary.csv")
+        sharded = [open(out + "/multibin/" + f).read() for f in files]
+        shutil.rmtree(out + "/multibin/diagnostic")
+        os.remove(out + "/multibin/sample/summary.csv")
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            sd.diagnoseSamples(out + "/multibin", nFigures=0)          # one process, all shards
+        assert buf.getvalue() == shardedStdout and len(shardedStdout) > 1000
+        assert [open(out + "/multibin/" + f).read() for f in files] == sharded
+        kb, binSamples, chainsB = sd.loadSamples(out + "/multibin/sample/")
+        assert kb == keys and chainsB == list(range(nChains))
+        numpy.testing.assert_allclose(binSamples, allSamples, rtol=0, atol=5.1e-7)   # the CSV files hold the same draws at "%f"
         # single-GPU reference run of the same global chains (no process group any more)
         ps.samplePosterior(nChains, nIter, nSamples, names, 24, nResp, "partial", handle, out + "/single",
                            saveLogLikelihood=False, startingPointValueRange=ranges, displayProgress=False)
