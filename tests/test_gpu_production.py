@@ -64,8 +64,8 @@ def _assertIdentical(prod, gen):
             same = (a == b) | (numpy.isnan(a) & numpy.isnan(b)) if a.dtype.kind == "f" else (a == b)
             assert same.all(), "%s differs in %d of %d entries" % (key, int((~same).sum()), same.size)
     assert numpy.isfinite(prod["theta"]).all()
-    # the chains moved and the step sizes were tuned: the comparison is not vacuous
-    assert (prod["scale"] != 1.0).mean() > 0.2
+    # step sizes were tuned and rows differ from one another: the comparison is not vacuous
+    assert (prod["scale"] != 1.0).any() and (prod["rows"][0] != prod["rows"][-1]).mean() > 0.5
 
 
 @pytest.mark.parametrize("label,R,ragged,pooling,noTc", [
