@@ -115,6 +115,9 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
+WRITER_THREADS = int(os.environ.get("MCMCN_STORE_THREADS", 4))     # host threads copying a chunk into the store file
+
+
 def retainedCount(lo, hi, burn, thin):
     """Number of iterations i in [lo, hi) that Sampler._loop retains (i >= burn and i % thin == 0, :887)."""
     first = -(-max(lo, burn) // thin) * thin
@@ -170,6 +173,9 @@ class SampleStore(object):
                            for _ in range(2)] if logLikelihood else None
             self._copied = [None, None]
             self._pending = []
+            import concurrent.futures
+            self._writers = concurrent.futures.ThreadPoolExecutor(max_workers=WRITER_THREADS)
+            self._rowsPerJob = max(1, -(-self.chunkRows // WRITER_THREADS))
             npdt = numpy.float64 if dtype == torch.float64 else numpy.float32
             self.sink = numpy.lib.format.open_memmap(path, mode="w+", dtype=npdt,
                                                      shape=(self.nRows, engine.nCol, engine.nChains))
@@ -225,7 +231,17 @@ class SampleStore(object):
         c, n, row0 = item
         self._copied[c].synchronize()
         nC = self.engine.nChains
-        self.sink[row0:row0 + n] = self._pin[c][:n].numpy()[:, :, :nC]
+        src = self._pin[c][:n].numpy()
+        # pinned memory -> the file's pages, a few rows per thread (numpy copies release the GIL; one thread
+        # alone is bound by first-touch page faults of the mapping)
+        parts = [(r, min(n, r + self._rowsPerJob)) for r in range(0, n, self._rowsPerJob)]
+
+        def put(span):
+            self.sink[row0 + span[0]:row0 + span[1]] = src[span[0]:span[1], :, :nC]
+        if len(parts) > 1:
+            list(self._writers.map(put, parts))
+        else:
+            put(parts[0])
         if self.logLik is not None and self.logLikSink is not None:
             self.logLikSink(row0, self._pinLL[c][:n].numpy()[:, :, :nC])
 
@@ -235,6 +251,7 @@ class SampleStore(object):
             self._flushChunk()
             while self._pending:
                 self._retire(self._pending.pop(0))
+            self._writers.shutdown()
             self.sink.flush()
         elif self.logLik is not None and self.logLikSink is not None:
             n = len(self.iterations)

@@ -334,6 +334,34 @@ def convergenceFromStore(storeTensor, nRows, nChains, group=None, timing=None):
     return rhat, ess
 
 
+def orderStatisticsFromStore(storeTensor, nRows, nChains, hdi_p=95, group=None, timing=None):
+    """numpy.median and the 95 % HDI (:419-427, :766-776) of every column of a device-resident sample
+    store, pooled over all chains and rows, in slabs of columns.  With ``group`` the pooled draws of a
+    slab go through the key-partitioned all-to-all (pooledMedianHdi): no rank ever holds all draws of all
+    columns.  Returns device [ncol][3] = median, HDI lower, HDI upper."""
+    n = int(nRows) // 2
+    ncol = storeTensor.shape[1]
+    dev = storeTensor.device
+    src = SampleSource(["c%d" % k for k in range(ncol)], [(storeTensor, list(range(nChains)))], 2 * n)
+    out = torch.empty((ncol, 3), dtype=torch.float64, device=dev)
+    step = _slabKeys(ncol, 2 * nChains, n)
+    exchanged = 0
+    for k0 in range(0, ncol, step):
+        k1 = min(ncol, k0 + step)
+        pooled = src.halfChains(k0, k1, dev).reshape(k1 - k0, 2 * nChains * n)
+        if group is not None:
+            import torch.distributed as dist
+            world = dist.get_world_size(group)
+            out[k0:k1] = pooledMedianHdi(pooled, hdi_p, group)
+            exchanged += pooled.numel() * 8 * (world - 1) // world          # what this rank sent to the other owners
+        else:
+            out[k0:k1] = _sortedMedianHdiDevice(pooled, hdi_p)
+        del pooled
+    if timing is not None:
+        timing["exchanged_bytes"] = exchanged
+    return out
+
+
 def chainRange(nChains, rank, world):
     """Contiguous global chain ids [lo, hi) of a rank."""
     return (nChains * rank) // world, (nChains * (rank + 1)) // world
