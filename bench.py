@@ -509,7 +509,10 @@ def fullRun(gpu, args, chainsTotal, nIter, nSamples, withDiagnostics):
         fin = numpy.isfinite(ess)
         rec["diagnostics"] = {"call": "sampleDiagnosis.Diagnostic(outputDirectory + '/sample/') -> rhat, effectiveN, median, hdi",
                               "keys": int(ess.size), "half_chains": int(diag._m), "draws_per_half_chain": int(diag._n),
-                              "max_rhat": float(numpy.nanmax(rhat)), "share_rhat_below_1.1": float(numpy.mean(rhat < 1.1)),
+                              "max_rhat": float(numpy.nanmax(rhat)), "max_rhat_key": diag._keys[int(numpy.nanargmax(rhat))],
+                              "share_rhat_below_1.1": float(numpy.mean(rhat < 1.1)),
+                              "keys_rhat_above_1.1": [diag._keys[i] for i in numpy.nonzero(~(rhat < 1.1))[0][:8]],
+                              "min_ess_key": diag._keys[int(numpy.argmin(numpy.where(fin, ess, numpy.inf)))],
                               "min_ess": float(ess[fin].min()), "median_ess": float(numpy.median(ess[fin])),
                               "seconds": diagS}
         rec["min_ess_per_s"] = rec["diagnostics"]["min_ess"] / wall

@@ -115,7 +115,7 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
-WRITER_THREADS = int(os.environ.get("MCMCN_STORE_THREADS", 4))     # host threads copying a chunk into the store file
+WRITER_THREADS = int(os.environ.get("MCMCN_STORE_THREADS", max(2, min(8, (os.cpu_count() or 4) // 2))))     # host threads copying a chunk into the store file
 
 
 def retainedCount(lo, hi, burn, thin):
@@ -175,7 +175,6 @@ class SampleStore(object):
             self._pending = []
             import concurrent.futures
             self._writers = concurrent.futures.ThreadPoolExecutor(max_workers=WRITER_THREADS)
-            self._rowsPerJob = max(1, -(-self.chunkRows // WRITER_THREADS))
             npdt = numpy.float64 if dtype == torch.float64 else numpy.float32
             self.sink = numpy.lib.format.open_memmap(path, mode="w+", dtype=npdt,
                                                      shape=(self.nRows, engine.nCol, engine.nChains))
@@ -232,16 +231,21 @@ class SampleStore(object):
         self._copied[c].synchronize()
         nC = self.engine.nChains
         src = self._pin[c][:n].numpy()
-        # pinned memory -> the file's pages, a few rows per thread (numpy copies release the GIL; one thread
-        # alone is bound by first-touch page faults of the mapping)
-        parts = [(r, min(n, r + self._rowsPerJob)) for r in range(0, n, self._rowsPerJob)]
+        # pinned memory -> the file's pages on WRITER_THREADS host threads (numpy copies release the GIL; one
+        # thread alone is bound by first-touch page faults of the mapping): whole rows per job when the chunk
+        # has many rows, column ranges of a row when it has few
+        ncol = src.shape[1]
+        perRow = max(1, -(-WRITER_THREADS // n))
+        colStep = -(-ncol // perRow)
+        jobs = [(r, k0, min(ncol, k0 + colStep)) for r in range(n) for k0 in range(0, ncol, colStep)]
 
-        def put(span):
-            self.sink[row0 + span[0]:row0 + span[1]] = src[span[0]:span[1], :, :nC]
-        if len(parts) > 1:
-            list(self._writers.map(put, parts))
+        def put(job):
+            r, k0, k1 = job
+            self.sink[row0 + r, k0:k1] = src[r, k0:k1, :nC]
+        if len(jobs) > 1:
+            list(self._writers.map(put, jobs))
         else:
-            put(parts[0])
+            put(jobs[0])
         if self.logLik is not None and self.logLikSink is not None:
             self.logLikSink(row0, self._pinLL[c][:n].numpy()[:, :, :nC])
 
@@ -516,9 +520,8 @@ class Engine(object):
         mu = x.copy()
         sigma2 = numpy.sqrt(numpy.abs(x) / 10.)                  # sic (:730)
         sd = numpy.sqrt(sigma2)
-        for c in range(nC):
-            for p in range(P):
-                theta[p, :, c] = rss[c].standard_normal(G) * sd[p, c] + mu[p, c]
+        for c in range(nC):      # name-major, group-minor: one call draws what P calls of G would (the stream is sequential)
+            theta[:, :, c] = rss[c].standard_normal((P, G)) * sd[:, c, None] + mu[:, c, None]
         lprior = hostNormLogpdf(theta, mu[:, None, :], sd[:, None, :])
         self.setState(theta, numpy.full((G, nC), numpy.nan), lprior, mu, sigma2)
         ll = numpy.full((G, nC), numpy.nan)

@@ -51,9 +51,10 @@ def main():
     dShard = sd.Diagnostic(samples=mine, keys=keys, group=dist.group.WORLD)
     rhat, ess, med, hdi = dShard.rhat, dShard.effectiveN, dShard.median, dShard.hdi
     # 3. sharded binary store
-    ps.CSV_VALUE_LIMIT = 0
+    csvLimit, ps.CSV_VALUE_LIMIT = ps.CSV_VALUE_LIMIT, 0
     ps.samplePosterior(nChains, nIter, nSamples, names, 24, nResp, "partial", handle, out + "/multibin",
                        saveLogLikelihood=False, startingPointValueRange=ranges, displayProgress=False)
+    ps.CSV_VALUE_LIMIT = csvLimit
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
         sd.diagnoseSamples(out + "/multibin", nFigures=0)
