@@ -117,10 +117,11 @@ typedef struct mcmcn_model {
     const double* obj_const;     /* device objective constants (gaussian_distribution: sd[P], log sd[P];
                                     linear_regression: bbar[G][K]) */
     const void* user_objective;  /* handle from mcmcn_user_objective_compile, or NULL */
-    /* Tensor-core operand blocks (linear_regression, precision 32, K <= 8; NULL = not provided, the
-     * FP32-pipe kernel is used).  Block of group g at float offset tc_group_off[g]: three slabs of
-     * [Np][8] floats, Np = R rounded up to 16 (at least 16): X_hi, X_lo, NE, where x = x_hi + x_lo
-     * with both parts rounded to TF32, and NE row n = (ne_hi, ne_mid, ne_lo, 0, 0, 0, 0, 0) with
+    /* Tensor-core operand blocks (linear_regression, precision 32, K <= 16; NULL = not provided, the
+     * FP32-pipe kernel is used).  Block of group g at float offset tc_group_off[g]: 2 KB + 1 slabs of
+     * [Np][8] floats, Np = R rounded up to 16 (at least 16), KB = 1 for K <= 8 and 2 for K = 9..16:
+     * X_hi of coefficients 0-7 (then 8-15), X_lo likewise, NE, where x = x_hi + x_lo with both parts
+     * rounded to TF32, and NE row n = (ne_hi, ne_mid, ne_lo, 0, 0, 0, 0, 0) with
      * ne = ne_hi + ne_mid + ne_lo exactly.  Within a slab element (n, k) sits at float index
      * (n/8)*64 + (k/4)*32 + (n%8)*4 + (k%4): the K-major, no-swizzle shared-memory layout that
      * tcgen05.mma reads (8-row x 16-byte core matrices).  Padding rows and coefficients are zero. */
@@ -200,7 +201,7 @@ int mcmcn_tile_capacity_bytes(void);
 int mcmcn_supported(int objective, int n_params, int n_coef, int precision);
 
 /* Will mcmcn_run advance this model with the tcgen05 step kernel (1) or the FP32-pipe kernel (0)?
- * (linear_regression, precision 32, K <= 8, tc_data given, every group block within the stage
+ * (linear_regression, precision 32, K <= 16, tc_data given, every group block within the stage
  * capacity; environment variable MCMCN_NO_TC=1 forces 0.) */
 int mcmcn_uses_tensor_core(const mcmcn_model* model);
 

@@ -45,7 +45,8 @@ static cudaError_t launch_sweep(sweep_fn fn, dim3 grid, dim3 block, size_t smem,
 
 static const KernelSet* find_set(int objective, int P, int K, int precision) {
     typedef const KernelSet* (*getter)(int*);
-    static const getter getters[] = {sets_linreg_a, sets_linreg_b, sets_linreg_c, sets_linreg_d, sets_linreg_e, sets_logit, sets_gauss};
+    static const getter getters[] = {sets_linreg_a, sets_linreg_b, sets_linreg_c, sets_linreg_d, sets_linreg_e,
+                                     sets_linreg_f, sets_linreg_g, sets_linreg_h, sets_linreg_i, sets_logit, sets_gauss};
     for (getter get : getters) {
         int n = 0;
         const KernelSet* sets = get(&n);
@@ -128,7 +129,7 @@ static int fill_args(SweepArgs& a, const KernelSet* ks, const mcmcn_model* m, co
 // groups.  Ranges are sized so that the grid is a whole number of 2-CTA-per-SM waves when it is
 // small and at most 32 groups long when it is large.
 static bool tc_eligible(const mcmcn_model* m) {
-    return m->objective == MCMCN_OBJ_LINEAR_REGRESSION && m->precision == 32 && m->n_coef <= 8 && m->tc_data &&
+    return m->objective == MCMCN_OBJ_LINEAR_REGRESSION && m->precision == 32 && m->n_coef <= 16 && m->tc_data &&
            m->tc_group_off && m->tc_max_block_floats > 0 && m->tc_max_block_floats * 4 <= kTcStageCapBytes &&
            !getenv("MCMCN_NO_TC");
 }
@@ -136,6 +137,7 @@ static bool tc_eligible(const mcmcn_model* m) {
 // the host copy of the FP32-pipe block table: a linear-regression block is ceil(R / 4) quads of
 // 4 * KP + 4 elements.
 static bool tc_uniform208(const mcmcn_model* m) {
+    if (m->n_coef > 8) return false;                                  // one K block only (mcmcn_tc.cuh)
     const long long unit = 4LL * ((m->n_coef + 3) & ~3) + 4;
     for (int g = 0; g < m->n_groups; ++g) {
         const long long quads = (m->group_off_host[g + 1] - m->group_off_host[g]) / unit;
@@ -337,9 +339,10 @@ int mcmcn_run(const mcmcn_model* m, const mcmcn_state* s, const mcmcn_run_args* 
                 (int)tc, (int)fast, (int)g.wide, (int)g.all_fit, (const void*)r->tape_z, (void*)r->trace_ll, (const void*)r->tape_accept,
                 r->use_lprior_override, (int)partial, g.smem, g.grid.x, g.grid.y, g.block.x);
     const bool u208 = tc && tc_uniform208(m);
-    const sweep_fn general = tc ? tc_sweep_kernel(-1, u208) : (g.wide ? ks->sweep_wide : ks->sweep_one);
+    const int kb = m->n_coef > 8 ? 2 : 1;                             // K blocks of 8 coefficients
+    const sweep_fn general = tc ? tc_sweep_kernel(-1, u208, kb) : (g.wide ? ks->sweep_wide : ks->sweep_one);
     sweep_fn fast_fn[4];
-    for (int f = 0; f < 4; ++f) fast_fn[f] = tc ? tc_sweep_kernel(f, u208) : ks->sweep_fast[f];
+    for (int f = 0; f < 4; ++f) fast_fn[f] = tc ? tc_sweep_kernel(f, u208, kb) : ks->sweep_fast[f];
     rc = set_smem_attr((const void*)general, g.smem);
     for (int f = 0; f < 4 && !rc; ++f) rc = set_smem_attr((const void*)fast_fn[f], g.smem);
     if (rc) return rc;

@@ -34,8 +34,13 @@ const KernelSet* sets_linreg_b(int* n);
 const KernelSet* sets_linreg_c(int* n);
 const KernelSet* sets_linreg_d(int* n);
 const KernelSet* sets_linreg_e(int* n);
+const KernelSet* sets_linreg_f(int* n);
+const KernelSet* sets_linreg_g(int* n);
+const KernelSet* sets_linreg_h(int* n);
+const KernelSet* sets_linreg_i(int* n);
 const KernelSet* sets_logit(int* n);
 const KernelSet* sets_gauss(int* n);
-sweep_fn tc_sweep_kernel(int f, bool uniform208);    // mcmcn_sets_tc.cu
+sweep_fn tc_sweep_kernel(int f, bool uniform208, int k_blocks);    // mcmcn_sets_tc.cu (one K block), mcmcn_sets_tc2.cu (two)
+sweep_fn tc_sweep_kernel_two_blocks(int f);
 
 }  // namespace mcmcn

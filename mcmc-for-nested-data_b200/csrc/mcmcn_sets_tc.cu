@@ -5,7 +5,8 @@
 namespace mcmcn {
 // f = MCMCN_F_PARTIAL | MCMCN_F_COUNT for the production variants, -1 for the general kernel;
 // uniform208: every group pads to 208 observations (see sweep_tc_kernel)
-sweep_fn tc_sweep_kernel(int f, bool uniform208) {
+sweep_fn tc_sweep_kernel(int f, bool uniform208, int k_blocks) {
+    if (k_blocks == 2) return tc_sweep_kernel_two_blocks(f);
     if (uniform208) {
         switch (f) {
             case 0: return sweep_tc_kernel<0, true>;

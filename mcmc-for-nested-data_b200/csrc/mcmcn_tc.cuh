@@ -28,6 +28,16 @@
 
 #include "mcmcn_device.cuh"
 
+// -DMCMCN_DEBUG_BOUNDS: device-side asserts on every tensor-memory column, shared-memory stage and TMA
+// extent the kernel computes (compute-sanitizer is not available on the GPU pool; build with
+// `python __graft_entry__.py --debug-bounds` -> libmcmcn_debug.so, run the tests with MCMCN_LIB pointing at it).
+#ifdef MCMCN_DEBUG_BOUNDS
+#include <cassert>
+#define MCMCN_CHECK(cond) assert(cond)
+#else
+#define MCMCN_CHECK(cond) ((void)0)
+#endif
+
 namespace mcmcn {
 
 // ---------------------------------------------------------------- tcgen05 / TMEM PTX
@@ -82,12 +92,16 @@ __device__ __forceinline__ unsigned tc_idesc(int M, int N) {
 // nearest TF32 (10 explicit mantissa bits) of an FP32 value, as bits
 __device__ __forceinline__ unsigned tf32_rn(float v) { return (__float_as_uint(v) + 0x1000u) & 0xFFFFE000u; }
 
-// TMEM column map of one CTA: 128 columns -> four CTAs per SM
-#define MCMCN_TC_CH 112        /* observations (columns) of the accumulator */
+// TMEM column map of one CTA: 128 columns -> four CTAs per SM.  KB = number of K blocks of 8 coefficients
+// (1: K <= 8, 2: K = 9..16): the accumulator takes what the A operand (hi and lo parts, 8 columns per K block
+// each) leaves -- 112 observations per chunk for KB = 1, 96 for KB = 2.
 #define MCMCN_TC_D 0
-#define MCMCN_TC_A_HI 112
-#define MCMCN_TC_A_LO 120
 #define MCMCN_TC_COLS 128
+template <int KB> struct TcMap {
+    static constexpr int CH = MCMCN_TC_COLS - 16 * KB;     /* observations (columns) of the accumulator */
+    static constexpr int A_HI = CH;
+    static constexpr int A_LO = CH + 8 * KB;
+};
 #define MCMCN_TC_THREADS 128
 #define MCMCN_TC_ONES_BYTES 4096   /* [128][8] constant A operand of the ne MMA, in shared memory */
 
@@ -105,19 +119,29 @@ __device__ __forceinline__ void mma_tf32_ss(unsigned d, unsigned long long adesc
         "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-// The 4 MMAs of observation chunk c of the block staged at `stage` (shared-memory address);
-// completion is signalled on `mbar`.
+// The 3 KB + 1 MMAs of observation chunk c of the block staged at `stage` (shared-memory address): per K
+// block A_hi.X_hi + A_lo.X_hi + A_hi.X_lo, then 1.(ne_hi, ne_mid, ne_lo).  The block holds the slabs
+// [X_hi block 0 .. KB-1 | X_lo block 0 .. KB-1 | NE], np * 32 bytes each.  Completion is signalled on `mbar`.
+template <int KB>
 __device__ __forceinline__ void tc_issue_chunk(unsigned tbase, unsigned stage, unsigned ones, int np, int c, unsigned mbar) {
-    const int row0 = c * MCMCN_TC_CH;
-    const int nc = min(MCMCN_TC_CH, np - row0);
+    typedef TcMap<KB> M;
+    const int row0 = c * M::CH;
+    const int nc = min(M::CH, np - row0);
+    MCMCN_CHECK(c >= 0 && row0 < np && nc >= 16 && (nc & 15) == 0 && nc <= M::CH);               // accumulator columns
+    MCMCN_CHECK(MCMCN_TC_D + nc <= M::A_HI && M::A_LO + 8 * KB <= MCMCN_TC_COLS);
+    MCMCN_CHECK((stage & 1023u) == 0u && (ones & 1023u) == 0u);                                    // descriptor bases
     const unsigned idesc = tc_idesc(128, nc);
     const unsigned slab = (unsigned)np * 32u;
     const unsigned base = stage + (unsigned)row0 * 32u;
     const unsigned d = tbase + MCMCN_TC_D;
-    mma_tf32_ts(d, tbase + MCMCN_TC_A_HI, tc_smem_desc(base, 128, 256), idesc, 0);               // A_hi . X_hi
-    mma_tf32_ts(d, tbase + MCMCN_TC_A_LO, tc_smem_desc(base, 128, 256), idesc, 1);               // A_lo . X_hi
-    mma_tf32_ts(d, tbase + MCMCN_TC_A_HI, tc_smem_desc(base + slab, 128, 256), idesc, 1);        // A_hi . X_lo
-    mma_tf32_ss(d, tc_smem_desc(ones, 128, 256), tc_smem_desc(base + 2 * slab, 128, 256), idesc, 1);   // 1 . (ne_hi, ne_mid, ne_lo)
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb) {
+        const unsigned long long xhi = tc_smem_desc(base + kb * slab, 128, 256), xlo = tc_smem_desc(base + (KB + kb) * slab, 128, 256);
+        mma_tf32_ts(d, tbase + M::A_HI + 8 * kb, xhi, idesc, kb ? 1 : 0);                         // A_hi . X_hi
+        mma_tf32_ts(d, tbase + M::A_LO + 8 * kb, xhi, idesc, 1);                                  // A_lo . X_hi
+        mma_tf32_ts(d, tbase + M::A_HI + 8 * kb, xlo, idesc, 1);                                  // A_hi . X_lo
+    }
+    mma_tf32_ss(d, tc_smem_desc(ones, 128, 256), tc_smem_desc(base + 2 * KB * slab, 128, 256), idesc, 1);   // 1 . (ne_hi, ne_mid, ne_lo)
     mma_commit(mbar);
 }
 
@@ -278,8 +302,12 @@ __device__ __forceinline__ bool tc_rendezvous_issuer() {
 // read-back is written for exactly two accumulator chunks of 112 + 96 columns.  Otherwise groups of
 // 113-224 observations take the same straight-line path with the second chunk looped, the rest the
 // chunk loop.  (One kernel with all three paths measured 2.4 % slower on the 208 case.)
-template <int F, bool UNIFORM208>
+// KB: K blocks of 8 coefficients (2 for K = 9..16: 7 MMAs per chunk of 96 observations; UNIFORM208 is a KB = 1 path).
+template <int F, bool UNIFORM208, int KB = 1>
 __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const SweepArgs a) {
+    static_assert(KB == 1 || !UNIFORM208, "the straight-line 112 + 96 read-back is for one K block");
+    typedef TcMap<KB> M;
+    constexpr int CH = M::CH;
     constexpr bool GENERAL = F < 0;
     const bool partial = GENERAL ? (a.partial != 0) : ((F & MCMCN_F_PARTIAL) != 0);
     const bool count = GENERAL ? (a.count != 0) : ((F & MCMCN_F_COUNT) != 0);
@@ -326,6 +354,8 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
     auto stage_group = [&](int s, int g) {                             // thread 0 only
         const long long e0 = a.tc_group_off[g], e1 = a.tc_group_off[g + 1];
         const unsigned bytes = (unsigned)((e1 - e0) * 4);
+        MCMCN_CHECK(s >= 0 && s < a.tc_stages && g >= g0 && g < g1);
+        MCMCN_CHECK(bytes > 0 && (bytes & 15u) == 0u && (int)bytes <= a.tc_stage_bytes && ((e0 * 4) & 15) == 0);   // TMA extent
         mbar_expect_tx(mb_tma0 + 8u * s, bytes);
         tma_bulk_g2s(stage0 + (unsigned)s * (unsigned)a.tc_stage_bytes, tc + e0, bytes, mb_tma0 + 8u * s);
     };
@@ -346,7 +376,10 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
         const int s = a.tc_stages > 1 ? ((g - g0) & 1) : 0;
         const int R = a.group_nobs[g];
         const int np = max(16, (R + 15) & ~15);                        // padded observation count of the block
-        const int nchunks = (np + MCMCN_TC_CH - 1) / MCMCN_TC_CH;
+        const int nchunks = (np + CH - 1) / CH;
+        MCMCN_CHECK(R >= 0 && np * 32 * (2 * KB + 1) == (int)((a.tc_group_off[g + 1] - a.tc_group_off[g]) * 4));   // 2 KB + 1 slabs of [np][8] floats
+        MCMCN_CHECK(np * 32 * (2 * KB + 1) <= a.tc_stage_bytes && (tbase & 0xFFFFu) + MCMCN_TC_COLS <= 512u);
+        MCMCN_CHECK(K >= 1 && K <= 8 * KB);
         const unsigned stage = stage0 + (unsigned)s * (unsigned)a.tc_stage_bytes;
         const double* bbar = a.obj_const + (size_t)g * K;
 
@@ -366,18 +399,22 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
         // the A operand go out in one two-column store.
         double prop = __dadd_rn(in.cur, __dmul_rn(in.sc, in.z));      // numpy.random.normal(value, sd), :304-306
         float wcur = (float)__dsub_rn(in.cur, in.bbar), wprop = (float)__dsub_rn(prop, in.bbar);
-        {   // A operand of the current state: centred coefficients (FP32), split hi / lo
-            unsigned hi[8], lo[8];
+        {   // A operand of the current state: centred coefficients (FP32), split hi / lo, 8 columns per K block
             const double* tk = tg;
 #pragma unroll
-            for (int k = 0; k < 8; ++k, tk += GS) {
-                float b = k < K ? (float)__dsub_rn(*tk, bbar[k]) : 0.0f;
-                if (k == 0) b = wprop;                                 // column 0 already holds sweep 0's proposal
-                hi[k] = tf32_rn(b);
-                lo[k] = tf32_rn(b - __uint_as_float(hi[k]));
+            for (int kb = 0; kb < KB; ++kb) {
+                unsigned hi[8], lo[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j, tk += GS) {
+                    const int k = 8 * kb + j;
+                    float b = k < K ? (float)__dsub_rn(*tk, bbar[k]) : 0.0f;
+                    if (k == 0) b = wprop;                             // column 0 already holds sweep 0's proposal
+                    hi[j] = tf32_rn(b);
+                    lo[j] = tf32_rn(b - __uint_as_float(hi[j]));
+                }
+                tmem_st8(tlane + M::A_HI + 8 * kb, hi);
+                tmem_st8(tlane + M::A_LO + 8 * kb, lo);
             }
-            tmem_st8(tlane + MCMCN_TC_A_HI, hi);
-            tmem_st8(tlane + MCMCN_TC_A_LO, lo);
         }
         double aux_m, aux_r;                                           // LinReg::Aux of the current sigma
         tc_sigma_terms(tg[(size_t)K * GS], R, aux_m, aux_r);
@@ -406,7 +443,7 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
             const float wcur_now = wcur, wprop_now = wprop;            // this sweep's; wcur / wprop move on to the next below
             if (is_sigma) tc_sigma_terms(prop, R, m_prop, r_prop);     // LinReg::aux of the proposed sigma
             tmem_wait_st();
-            if (tc_rendezvous_issuer()) tc_issue_chunk(tbase, stage, ones, np, 0, mb_mma);
+            if (tc_rendezvous_issuer()) tc_issue_chunk<KB>(tbase, stage, ones, np, 0, mb_mma);
             // while the tensor core works: state and random numbers of the next sweep.  (Drawing the
             // random numbers inside the read-back code instead, to fill its tensor-memory latency, cost
             // registers and measured 8 % slower.)
@@ -421,30 +458,30 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
                 mbar_wait(mb_mma, mma_phase);
                 tc_fence_after();
                 tc_accumulate_fixed<7>(tlane + MCMCN_TC_D, sq);
-                if (tc_rendezvous_issuer()) tc_issue_chunk(tbase, stage, ones, np, 1, mb_mma);
+                if (tc_rendezvous_issuer()) tc_issue_chunk<KB>(tbase, stage, ones, np, 1, mb_mma);
                 mbar_wait(mb_mma, mma_phase ^ 1u);
                 tc_fence_after();
                 tc_accumulate_fixed<6>(tlane + MCMCN_TC_D, sq);
                 acc = (double)((sum2(sq[0]) + sum2(sq[1])) + (sum2(sq[2]) + sum2(sq[3])));
-            } else if (!UNIFORM208 && nchunks == 2) {                  // any group of 113-224 observations: the same, second chunk looped
+            } else if (!UNIFORM208 && KB == 1 && nchunks == 2) {       // any group of 113-224 observations: the same, second chunk looped
                 f32x2 sq[4] = {0ull, 0ull, 0ull, 0ull};
                 mbar_wait(mb_mma, mma_phase);
                 tc_fence_after();
                 tc_accumulate_fixed<7>(tlane + MCMCN_TC_D, sq);
-                if (tc_rendezvous_issuer()) tc_issue_chunk(tbase, stage, ones, np, 1, mb_mma);
+                if (tc_rendezvous_issuer()) tc_issue_chunk<KB>(tbase, stage, ones, np, 1, mb_mma);
                 mbar_wait(mb_mma, mma_phase ^ 1u);
                 tc_fence_after();
-                tc_accumulate_any(tlane + MCMCN_TC_D, (np - MCMCN_TC_CH) >> 4, sq);
+                tc_accumulate_any(tlane + MCMCN_TC_D, (np - CH) >> 4, sq);
                 acc = (double)((sum2(sq[0]) + sum2(sq[1])) + (sum2(sq[2]) + sum2(sq[3])));
             } else
             for (int c = 0; c < nchunks; ++c) {
                 mbar_wait(mb_mma, mma_phase);
                 mma_phase ^= 1u;
                 tc_fence_after();
-                const int nc = min(MCMCN_TC_CH, np - c * MCMCN_TC_CH);
+                const int nc = min(CH, np - c * CH);
                 acc += tc_sum_squares(tlane + MCMCN_TC_D, nc >> 4);
                 if (c + 1 < nchunks) {                                 // the accumulator is free once every lane has read it
-                    if (tc_rendezvous_issuer()) tc_issue_chunk(tbase, stage, ones, np, c + 1, mb_mma);
+                    if (tc_rendezvous_issuer()) tc_issue_chunk<KB>(tbase, stage, ones, np, c + 1, mb_mma);
                 }
             }
 
@@ -480,15 +517,16 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
                 const float wkeep = accept ? wprop_now : wcur_now;
                 const unsigned h = tf32_rn(wkeep), l = tf32_rn(wkeep - __uint_as_float(h));
                 prop = __dadd_rn(in.cur, __dmul_rn(in.sc, in.z));      // `in` holds sweep p + 1 by now
+                MCMCN_CHECK(p >= 0 && p < 8 * KB && p < K);                             // A-operand column
                 if (p + 1 < K) {
                     wcur = (float)__dsub_rn(in.cur, in.bbar);
                     wprop = (float)__dsub_rn(prop, in.bbar);
                     const unsigned nh = tf32_rn(wprop);
-                    tmem_st2(tlane + MCMCN_TC_A_HI + p, h, nh);
-                    tmem_st2(tlane + MCMCN_TC_A_LO + p, l, tf32_rn(wprop - __uint_as_float(nh)));
+                    tmem_st2(tlane + M::A_HI + p, h, nh);
+                    tmem_st2(tlane + M::A_LO + p, l, tf32_rn(wprop - __uint_as_float(nh)));
                 } else {                                               // the next sweep is sigma's: no column of its own
-                    tmem_st1(tlane + MCMCN_TC_A_HI + p, h);
-                    tmem_st1(tlane + MCMCN_TC_A_LO + p, l);
+                    tmem_st1(tlane + M::A_HI + p, h);
+                    tmem_st1(tlane + M::A_LO + p, l);
                 }
             }
             if (count && on) {

@@ -201,16 +201,17 @@ class Objective(object):
         self.tcData = self.tcGroupOff = None
         if self.kind == nat.OBJ_LINEAR_REGRESSION:
             obj_const = numpy.ascontiguousarray(bbar.reshape(-1))
-            if self.precision == "fp32" and self.nCoef <= 8:
+            if self.precision == "fp32" and self.nCoef <= 16:
                 self.tcData, self.tcGroupOff = self._packTensorCore(nResp, bbar)
         if self.kind == nat.OBJ_GAUSSIAN_DISTRIBUTION:
             obj_const = numpy.concatenate([self.sd, numpy.log(self.sd)]).astype(numpy.float64)
         return data, group_off, numpy.array(nResp, dtype=numpy.int32), obj_const
 
     def _packTensorCore(self, nResp, bbar):
-        """Operand blocks of the tcgen05 step kernel (include/mcmcn.h, mcmcn_model.tc_data): per
-        group three slabs [Np][8] -- X_hi, X_lo, NE -- in the K-major no-swizzle core-matrix layout,
-        the FP32 values split into parts that are exact in TF32 (3xTF32)."""
+        """Operand blocks of the tcgen05 step kernel (include/mcmcn.h, mcmcn_model.tc_data): per group the
+        slabs X_hi (one per block of 8 coefficients: one for K <= 8, two for K = 9..16), X_lo (likewise)
+        and NE, each [Np][8] in the K-major no-swizzle core-matrix layout, the FP32 values split into
+        parts that are exact in TF32 (3xTF32)."""
         def tf32(v):
             bits = numpy.ascontiguousarray(v, dtype=numpy.float32).view(numpy.uint32)
             return ((bits + numpy.uint32(0x1000)) & numpy.uint32(0xFFFFE000)).view(numpy.float32)
@@ -219,15 +220,17 @@ class Objective(object):
             return a.reshape(a.shape[0] // 8, 8, 2, 4).transpose(0, 2, 1, 3).reshape(-1)
 
         K = self.nCoef
+        KB = 1 if K <= 8 else 2
+        nSlabs = 2 * KB + 1
         npad = [max(16, (r + 15) // 16 * 16) for r in nResp]
         off = numpy.zeros(len(nResp) + 1, dtype=numpy.int64)
-        off[1:] = numpy.cumsum(numpy.array(npad, dtype=numpy.int64) * 24)
+        off[1:] = numpy.cumsum(numpy.array(npad, dtype=numpy.int64) * 8 * nSlabs)
         data = numpy.zeros(int(off[-1]), dtype=numpy.float32)
         start = 0
         for g, r in enumerate(nResp):
             n = npad[g]
             Xg, yg = self.X[start:start + r], self.y[start:start + r]
-            x = numpy.zeros((n, 8), dtype=numpy.float32)
+            x = numpy.zeros((n, 8 * KB), dtype=numpy.float32)
             x[:r, :K] = Xg
             ne = numpy.zeros(n, dtype=numpy.float32)
             ne[:r] = Xg @ bbar[g] - yg                  # same FP32 values as the FP32-pipe block
@@ -238,9 +241,10 @@ class Objective(object):
             nes[:, 1] = tf32(ne - nes[:, 0])
             nes[:, 2] = (ne - nes[:, 0]) - nes[:, 1]
             blk = data[off[g]:off[g + 1]]
-            blk[:8 * n] = slab(xhi)
-            blk[8 * n:16 * n] = slab(xlo)
-            blk[16 * n:] = slab(nes)
+            for kb in range(KB):
+                blk[8 * n * kb:8 * n * (kb + 1)] = slab(xhi[:, 8 * kb:8 * kb + 8])
+                blk[8 * n * (KB + kb):8 * n * (KB + kb + 1)] = slab(xlo[:, 8 * kb:8 * kb + 8])
+            blk[8 * n * 2 * KB:] = slab(nes)
             start += r
         return data, off
 

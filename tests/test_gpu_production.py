@@ -69,6 +69,7 @@ def _assertIdentical(prod, gen):
 
 
 @pytest.mark.parametrize("label,R,ragged,pooling,noTc", [
+    ("tc-two-k-blocks", 200, False, "partial", False),   # K = 12: sweep_tc_kernel<F, false, 2>
     ("tc-uniform208", 200, False, "partial", False),     # C3's group shape: sweep_tc_kernel<F, true>
     ("tc-uniform208-fixed-priors", 200, False, "none", False),
     ("tc-any", 160, False, "partial", False),            # two chunks, second looped: sweep_tc_kernel<F, false>
@@ -78,7 +79,7 @@ def _assertIdentical(prod, gen):
 ])
 def test_production_regression_kernels_equal_general_bit_for_bit(label, R, ragged, pooling, noTc, monkeypatch):
     from engine import Engine
-    G, K, nC = 12, 8, 161
+    G, K, nC = 12, (12 if label == "tc-two-k-blocks" else 8), 161
     obj, names, nResp, ranges = parity.syntheticRegression(G=G, R=R, K=K, ragged=ragged)
     prior = [scipy.stats.norm(0, 10)] * K + [scipy.stats.gamma(2)] if pooling == "none" else None
     env = (("MCMCN_NO_TC", "1"),) if noTc else ()

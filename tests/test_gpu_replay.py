@@ -93,6 +93,9 @@ def test_replay_c3_shape_wide_path(precision, tol, tensorCore, monkeypatch):
     (3, 500, 8, False, "partial", 40),       # 48 KB blocks: one TMA stage, five accumulator chunks
     (4, 160, 8, False, "partial", 70),       # two chunks of 112 + 48: the straight-line read-back with a looped second chunk
     (5, 205, 3, True, "partial", 33),        # ragged groups of 1..409 observations: one, two and more chunks side by side
+    (4, 200, 12, False, "partial", 70),      # K = 9..16: two K blocks, accumulator chunks of 96 (96 + 96 + 16), 7 MMAs per chunk
+    (5, 100, 16, True, "partial", 33),       # all 16 coefficient columns, ragged groups of 1..199 observations
+    (3, 250, 9, False, "none", 130),         # one coefficient in the second K block, fixed priors, 33 KB blocks: one TMA stage
 ])
 def test_replay_tensor_core_kernel_shapes(G, R, K, ragged, pooling, nChains):
     """The tcgen05 step kernel over the shapes that change its control flow: number of
@@ -135,6 +138,23 @@ def test_tensor_core_and_fp32_pipe_kernels_agree_at_c3_size(monkeypatch):
     assert numpy.isfinite(out["tc"][0]).mean() > 0.99
     assert parity.relErr(out["tc"][0], out["pipe"][0]).max() <= 2e-5
     numpy.testing.assert_array_equal(out["tc"][1], out["pipe"][1])      # forced decisions: identical states
+
+
+def test_replay_more_than_8_coefficients_fp32_pipe_and_fp64(monkeypatch):
+    """K = 9..16 off the tensor core: the FP32-pipe kernel (two chains per lane) and the FP64 kernel
+    (trajectory-exact), LinReg<12>."""
+    obj, names, nResp, ranges = parity.syntheticRegression(G=5, R=60, K=12)
+    res = parity.replay(obj, names, 5, nResp, "partial", None, ranges, nChains=3, nIter=60, nSamples=20,
+                        precision="fp64", force=False)
+    err, ties = parity.checkReplay(res, 1e-11, 0.0)
+    assert ties == 0 and not res.engine.usesTensorCore
+    numpy.testing.assert_allclose(res.rows, res.oracleRows, rtol=1e-9, atol=1e-9)
+    monkeypatch.setenv("MCMCN_NO_TC", "1")
+    res = parity.replay(obj, names, 5, nResp, "partial", None, ranges, nChains=70, nIter=30, nSamples=10,
+                        precision="fp32")
+    assert not res.engine.usesTensorCore
+    parity.checkReplay(res, 1e-5, 1e-5)
+    numpy.testing.assert_allclose(res.rows, res.oracleRows, rtol=1e-9, atol=1e-9)
 
 
 @pytest.mark.parametrize("workload", ["c3-tcgen05", "c3-fp32-pipe", "c5"])

@@ -36,8 +36,11 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert lib.mcmcn_version() == 100
     assert lib.mcmcn_tile_capacity_bytes() == 65536
     assert lib.mcmcn_supported(nat.OBJ_LINEAR_REGRESSION, 9, 8, 32) == 1
-    assert lib.mcmcn_supported(nat.OBJ_LINEAR_REGRESSION, 7, 6, 32) == 1      # K = 1..8 are compiled in
-    assert lib.mcmcn_supported(nat.OBJ_LINEAR_REGRESSION, 11, 10, 32) == 0
+    assert lib.mcmcn_supported(nat.OBJ_LINEAR_REGRESSION, 7, 6, 32) == 1
+    for K in range(1, 17):                                                     # K = 1..16 are compiled in (mcmcn.h: K <= 16)
+        assert lib.mcmcn_supported(nat.OBJ_LINEAR_REGRESSION, K + 1, K, 32) == 1
+        assert lib.mcmcn_supported(nat.OBJ_LINEAR_REGRESSION, K + 1, K, 64) == 1
+    assert lib.mcmcn_supported(nat.OBJ_LINEAR_REGRESSION, 18, 17, 32) == 0
 
 
 def test_ctypes_structs_mirror_the_header(tmp_path):
