@@ -44,7 +44,7 @@ from workloads import makeWorkload, makeLogitWorkload  # noqa: E402
 
 METRIC = "chain-iterations/sec"
 UNIT = "chain-iterations/s"
-FLOP_PER_EVAL = 20.0      # 2K+4 at K=8 (DESIGN.md "algorithmic work")
+FLOP_PER_EVAL = 20.0      # 2K+4 at K=8 (DESIGN.md "algorithmic work"); 2K+4 for other K
 C4_CHAINS = 16384
 REF_RUNNER = os.path.join(ROOT, "baseline", "run_reference.py")
 REF_STAGED = os.path.join(ROOT, "baseline", "_ref", "posteriorSampling.py")
@@ -301,10 +301,10 @@ def roofline(args, tensorCore, sweepMs, chains, peakFp32, peakTf32, peakMufu):
                 "peak_source": "MUFU pipe limit measured in this run by an ex2-only microbenchmark (mcmcn_peak_mufu); "
                                "nominal 148 SM x 16 lanes x 1.965 GHz = 4653"}
     P, N = K + 1, G * R
-    algFlops = FLOP_PER_EVAL * P * N * chains
+    algFlops = (2.0 * K + 4.0) * P * N * chains
     algTflops = algFlops / (sweepMs * 1e-3) / 1e12
     key = "tc" if tensorCore else "pipe"
-    common = {"flop_per_eval": FLOP_PER_EVAL, "algorithmic_fp32_tflops": algTflops,
+    common = {"flop_per_eval": 2.0 * K + 4.0, "algorithmic_fp32_tflops": algTflops,
               "fp32_pipe_peak_tflops": peakFp32 / 1e12, "mufu_peak_gops": peakMufu / 1e9,
               "traffic": TRAFFIC[key][0] * scale,
               "traffic_source": TRAFFIC[key][1] + ", scaled by chains / 1,024; not measured live"}
@@ -316,7 +316,8 @@ def roofline(args, tensorCore, sweepMs, chains, peakFp32, peakTf32, peakMufu):
         return common
     npad = max(16, (R + 15) // 16 * 16)
     tiles = ((chains + 127) // 128) * G * P
-    tf32Flops = tiles * 4 * 2.0 * 128 * npad * 8
+    kBlocks = 1 if K <= 8 else 2                                    # 3 MMAs per block of 8 coefficients + the ne MMA
+    tf32Flops = tiles * (3 * kBlocks + 1) * 2.0 * 128 * npad * 8
     common.update({"bound": "tensor", "kernel": "sweep_tc_kernel (tcgen05.mma kind::tf32, 3xTF32 + ne)",
                    "achieved": tf32Flops / (sweepMs * 1e-3) / 1e12, "peak": peakTf32 / 1e12, "unit": "TFLOP/s",
                    "frac": tf32Flops / (sweepMs * 1e-3) / peakTf32,
