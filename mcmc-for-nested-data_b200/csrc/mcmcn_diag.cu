@@ -40,9 +40,12 @@ __global__ void moments_kernel(const double* __restrict__ x, long long rows, int
 }
 
 // Variogram numerators (:189-194): out[key][t] = sum_j sum_{i=t}^{n-1} (x[j][i]-x[j][i-t])^2.
-// Block = one key x one slab of lags; half-chains are staged through shared memory one at
-// a time and accumulated in half-chain order.  Thread `l` owns lags t0+l and, to balance
-// the triangular work, n-1-(t0+l) (lags are paired from both ends).
+// Block = one key x one slab of lags x one range of half-chains; the half-chains are staged through
+// shared memory one at a time and accumulated in half-chain order.  Thread `l` owns lags t0+l and, to
+// balance the triangular work, n-1-(t0+l) (lags are paired from both ends).  With several half-chain
+// ranges (gridDim.z > 1: a slab of few keys would otherwise leave most SMs idle -- 256 blocks for 128 keys,
+// 11 % of the warp slots, profiles/r2_variogram_kernel_ncu_summary.txt) the per-range sums go to
+// part[key][range][t] and variogram_fold_kernel adds them in range order: a fixed summation order.
 __global__ void variogram_kernel(const double* __restrict__ x, int m, int n, double* __restrict__ out) {
     extern __shared__ double row[];
     const long long key = blockIdx.x;
@@ -50,8 +53,10 @@ __global__ void variogram_kernel(const double* __restrict__ x, int m, int n, dou
     const int t = blockIdx.y * blockDim.x + threadIdx.x;
     const int ta = t, tb = n - 1 - t;
     const bool on = t < half;
+    const int nz = gridDim.z, z = blockIdx.z;
+    const int j0 = (int)(((long long)m * z) / nz), j1 = (int)(((long long)m * (z + 1)) / nz);
     double sa = 0.0, sb = 0.0;
-    for (int j = 0; j < m; ++j) {
+    for (int j = j0; j < j1; ++j) {
         const double* p = x + (key * m + j) * (long long)n;
         __syncthreads();
         for (int i = threadIdx.x; i < n; i += blockDim.x) row[i] = p[i];
@@ -68,9 +73,19 @@ __global__ void variogram_kernel(const double* __restrict__ x, int m, int n, dou
         }
     }
     if (on) {
-        out[key * n + ta] = sa;
-        if (tb != ta) out[key * n + tb] = sb;
+        double* o = out + (key * nz + z) * (long long)n;
+        o[ta] = sa;
+        if (tb != ta) o[tb] = sb;
     }
+}
+__global__ void variogram_fold_kernel(const double* __restrict__ part, int nz, int n, long long total, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // key * n + t
+    if (i >= total) return;
+    const long long key = i / n, t = i - key * n;
+    const double* p = part + key * nz * (long long)n + t;
+    double s = 0.0;
+    for (int z = 0; z < nz; ++z) s += p[(long long)z * n];
+    out[i] = s;
 }
 
 // Median (numpy.median) and shortest interval of `gap` order statistics (:766-776) of one
@@ -222,16 +237,34 @@ int mcmcn_diag_moments(const double* x, int64_t n_keys, int32_t m, int32_t n, do
     return MCMCN_OK;
 }
 
-int mcmcn_diag_variogram(const double* x, int64_t n_keys, int32_t m, int32_t n, double* out, void* stream) {
+int mcmcn_diag_variogram(const double* x, int64_t n_keys, int32_t m, int32_t n, double* out, void* stream_) {
     if (!x || !out || n_keys < 1 || m < 1 || n < 2) { set_error("bad diag_variogram args"); return MCMCN_ERR_INVALID; }
+    cudaStream_t stream = (cudaStream_t)stream_;
     const size_t smem = sizeof(double) * (size_t)n;
     if (smem > 200 * 1024) { set_error("n=%d draws per half-chain exceed the shared-memory row buffer", n); return MCMCN_ERR_UNSUPPORTED; }
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(variogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int half = (n + 1) / 2;
     const int threads = half < 128 ? ((half + 31) & ~31) : 128;
-    const dim3 grid((unsigned)n_keys, (unsigned)((half + threads - 1) / threads), 1);
-    variogram_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(x, m, n, out);
-    CK(cudaGetLastError());
+    const unsigned lag_slabs = (unsigned)((half + threads - 1) / threads);
+    // ranges of half-chains: a function of m alone, so that a key's sums do not depend on how many keys share the
+    // launch (slabs of any size give bit-identical results): 64 half-chains per range, at most 16 ranges
+    int nz = m / 64;
+    if (nz < 1) nz = 1;
+    if (nz > 16) nz = 16;
+    const dim3 grid((unsigned)n_keys, lag_slabs, (unsigned)nz);
+    if (nz == 1) {
+        variogram_kernel<<<grid, threads, smem, stream>>>(x, m, n, out);
+        CK(cudaGetLastError());
+        return MCMCN_OK;
+    }
+    double* part = nullptr;
+    const long long total = (long long)n_keys * n;
+    CK(cudaMallocAsync((void**)&part, sizeof(double) * (size_t)total * nz, stream));
+    variogram_kernel<<<grid, threads, smem, stream>>>(x, m, n, part);
+    variogram_fold_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(part, nz, n, total, out);
+    const cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(part, stream);
+    CK(e);
     return MCMCN_OK;
 }
 

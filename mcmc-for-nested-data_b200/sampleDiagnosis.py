@@ -126,6 +126,7 @@ def computeHpdInterval(samples, hdi_p=95):
 
 # ------------------------------------------------------------------------------ where the draws come from
 SLAB_BYTES = int(os.environ.get("MCMCN_DIAG_SLAB_BYTES", 1 << 30))     # device bytes of half-chains per slab of keys
+STAGE_THREADS = int(os.environ.get("MCMCN_DIAG_THREADS", max(2, min(8, (os.cpu_count() or 4) // 2))))   # host threads staging a slab
 
 
 def _rankWorld():
@@ -148,6 +149,7 @@ class SampleSource(object):
         self.nRows = int(nRows)
         self.chains = [c for _, ids in blocks for c in ids]
         self.nChains = len(self.chains)
+        self._pins, self._pool, self._stageKeys = {}, None, 1
 
     @classmethod
     def fromArray(cls, samples, keys, chains=None):
@@ -157,22 +159,65 @@ class SampleSource(object):
         block = numpy.ascontiguousarray(numpy.transpose(samples, (1, 2, 0)))       # [rows][keys][chains]
         return cls(keys, [(block, list(chains) if chains is not None else list(range(nC)))], rows)
 
-    def halfChains(self, k0, k1, dev):
+    def stage(self, k0, k1, slot=0):
+        """Host half of halfChains: the columns k0..k1 of every host block (numpy array or memmap of a shard
+        file) copied into pinned memory, rows split over a few threads (numpy copies release the GIL; one
+        thread gathers about 4 GB/s out of a memory-mapped file).  Two slots, so that the next slab can be
+        staged while the device works on this one.  Returns one pinned tensor (or None: device block) per block."""
+        n = self.nRows // 2
+        out = []
+        for bi, (arr, ids) in enumerate(self.blocks):
+            if isinstance(arr, torch.Tensor):
+                out.append(None)
+                continue
+            nC, nk = len(ids), k1 - k0
+            tdt = torch.float64 if arr.dtype == numpy.float64 else torch.float32
+            key = (bi, slot)
+            pin = self._pins.get(key)
+            if pin is None or pin.dtype != tdt or pin.numel() < 2 * n * nk * nC:
+                pin = torch.empty((2 * n * max(nk, self._stageKeys) * nC,), dtype=tdt)
+                if torch.cuda.is_available():
+                    pin = pin.pin_memory()
+                self._pins[key] = pin
+            view = pin[:2 * n * nk * nC].view(2 * n, nk, nC)
+            dst = view.numpy()
+            rowsPer = max(1, -(-2 * n // STAGE_THREADS))
+            spans = [(r, min(2 * n, r + rowsPer)) for r in range(0, 2 * n, rowsPer)]
+
+            def copy(span, arr=arr, dst=dst, nC=nC):
+                dst[span[0]:span[1]] = arr[span[0]:span[1], k0:k1, :nC]
+            if len(spans) > 1:
+                list(self._threads().map(copy, spans))
+            else:
+                copy(spans[0])
+            out.append(view)
+        return out
+
+    def _threads(self):
+        if self._pool is None:
+            import concurrent.futures
+            self._pool = concurrent.futures.ThreadPoolExecutor(max_workers=STAGE_THREADS)
+        return self._pool
+
+    def halfChains(self, k0, k1, dev, staged=None):
         n = self.nRows // 2
         nk = k1 - k0
         out = torch.empty((nk, 2 * self.nChains, n), dtype=torch.float64, device=dev)
         st = _stream(dev)
+        if staged is None:
+            staged = self.stage(k0, k1)
         j0 = 0
-        for arr, ids in self.blocks:
+        for (arr, ids), host in zip(self.blocks, staged):
             nC = len(ids)
-            if isinstance(arr, torch.Tensor):                   # resident store: gather straight from it
+            if host is None:                                    # resident store: gather straight from it
                 src, ncol, stride, kk = arr, arr.shape[1], arr.shape[2], k0
             else:                                               # host rows: this slab of columns only
-                host = numpy.ascontiguousarray(arr[:2 * n, k0:k1, :nC])
-                src, ncol, stride, kk = torch.from_numpy(host).to(dev), nk, nC, 0
+                src, ncol, stride, kk = host.to(dev, non_blocking=True), nk, nC, 0
             nat.call("mcmcn_diag_halfchains", _ptr(src), 64 if src.dtype == torch.float64 else 32, n, ncol, stride,
                      kk, nk, nC, 2 * self.nChains, j0, _ptr(out), st)
             j0 += 2 * nC
+            if host is not None:
+                torch.cuda.current_stream(dev).synchronize()    # the pinned slot may be refilled once its copy has left
             del src
         return out
 
@@ -422,10 +467,17 @@ class Diagnostic(object):
         mh = numpy.empty((nKeys, 3))
         self._rhoArr = numpy.empty((nKeys, n))
         step = _slabKeys(nKeys, mL, n)
-        for k0 in range(0, nKeys, step):
-            k1 = min(nKeys, k0 + step)
+        self._source._stageKeys = step
+        import concurrent.futures
+        ahead = concurrent.futures.ThreadPoolExecutor(max_workers=1)
+        slabs = [(k0, min(nKeys, k0 + step)) for k0 in range(0, nKeys, step)]
+        pending = ahead.submit(self._source.stage, slabs[0][0], slabs[0][1], 0)
+        for i, (k0, k1) in enumerate(slabs):
             nk = k1 - k0
-            x = self._source.halfChains(k0, k1, dev)                   # [nk][mL][n]
+            staged = pending.result()
+            if i + 1 < len(slabs):                                     # the next slab's rows leave the files meanwhile
+                pending = ahead.submit(self._source.stage, slabs[i + 1][0], slabs[i + 1][1], (i + 1) & 1)
+            x = self._source.halfChains(k0, k1, dev, staged)           # [nk][mL][n]
             rh, vario, m = _convergenceSlab(x, self._group)
             ess = torch.empty((nk,), dtype=f64, device=dev)
             rho = torch.empty((nk, n), dtype=f64, device=dev)
@@ -438,6 +490,7 @@ class Diagnostic(object):
             rh_h[k0:k1], ess_h[k0:k1] = rh.cpu().numpy(), ess.cpu().numpy()
             self._rhoArr[k0:k1] = rho.cpu().numpy()
             del x, pooled
+        ahead.shutdown()
         k = self._keys
         self._B = dict(zip(k, rh_h[:, 0]))
         self._W = dict(zip(k, rh_h[:, 1]))

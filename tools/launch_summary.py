@@ -18,7 +18,7 @@ for r in rows[1:]:
     agg[r[ki]][1] += v
 tot = sum(v[1] for v in agg.values())
 print("# ncu launch list (cold-cache, serialised: compare SHARES, not absolutes)\n")
-print("command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv %s`\n" % sys.argv[2])
+print("command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv %s`\n" % sys.argv[2])
 print("| kernel | launches | total us | share |\n|---|---:|---:|---:|")
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print("| `%s` | %d | %.1f | %.1f%% |" % (k[:90], n, t, 100 * t / tot))
