@@ -71,6 +71,36 @@ def test_replay_mle_start_regression_example():
     numpy.testing.assert_allclose(res.rows, res.oracleRows, rtol=1e-9, atol=1e-9)
 
 
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_replay_c2_full_config_reproduces_the_reference_files(precision, tmp_path):
+    """BASELINE config 2 as the reference runs it (example.regression partial: 4 chains x 2,000 iterations,
+    nSamples 1,000, startWithMLE) in replay mode on the GPU: per-step log-densities and the accept
+    trajectory against the oracle, and the sample files written from the engine's retained rows must
+    be the reference's own files (sha256 of sample.<chain>.csv recorded by tests/golden/make_golden.py
+    from the unmodified reference)."""
+    import ast
+    import hashlib
+    import posteriorSampling as ps
+    meta, obj, prior = _goldenCase("c2_regression_partial")
+    names = tuple(meta["parameterName"])
+    res = parity.replay(obj, names, meta["nGroups"], meta["nResponsesPerGroup"], meta["pooling"], prior,
+                        meta["startingPointValueRange"], nChains=meta["nChains"], nIter=meta["nIter"],
+                        nSamples=meta["nSamples"], precision=precision, startWithMLE=meta["startWithMLE"])
+    if precision == "fp64":
+        err, ties = parity.checkReplay(res, 1e-11, 0.0)
+        assert ties == 0
+    else:
+        err, ties = parity.checkReplay(res, 1e-5, 1e-5)
+        assert ties <= 30, ties                      # of 240,000 decisions; teacher-forced
+    sha = meta["sha256"] if isinstance(meta["sha256"], dict) else ast.literal_eval(meta["sha256"])
+    header = ps.sampleHeader(names, meta["nGroups"], meta["pooling"])
+    assert len(res.store.iterations) == 1000
+    for c in range(meta["nChains"]):
+        path = str(tmp_path / ("sample.%d.csv" % c))
+        ps.writeSampleCsv(path, c, header, res.store.iterations, res.rows[:, :, c])
+        assert hashlib.sha256(open(path, "rb").read()).hexdigest() == sha["sample.%d.csv" % c], c
+
+
 @pytest.mark.parametrize("precision,tol,tensorCore", [("fp32", 1e-5, True), ("fp32", 1e-5, False), ("fp64", 1e-11, False)])
 def test_replay_c3_shape_wide_path(precision, tol, tensorCore, monkeypatch):
     """C3's shape (K = 8 coefficients + sigma, R = 200) on the tcgen05 step kernel (two
