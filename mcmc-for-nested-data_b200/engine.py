@@ -115,7 +115,13 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
-WRITER_THREADS = int(os.environ.get("MCMCN_STORE_THREADS", max(2, min(8, (os.cpu_count() or 4) // 2))))     # host threads copying a chunk into the store file
+def _hostThreads(env):
+    """Host copy threads of this process: an even share of the cores among the ranks of this box, 2..8."""
+    share = (os.cpu_count() or 4) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    return int(os.environ.get(env, max(2, min(8, share // 2))))
+
+
+WRITER_THREADS = _hostThreads("MCMCN_STORE_THREADS")
 
 
 def retainedCount(lo, hi, burn, thin):

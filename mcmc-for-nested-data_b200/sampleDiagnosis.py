@@ -126,7 +126,13 @@ def computeHpdInterval(samples, hdi_p=95):
 
 # ------------------------------------------------------------------------------ where the draws come from
 SLAB_BYTES = int(os.environ.get("MCMCN_DIAG_SLAB_BYTES", 1 << 30))     # device bytes of half-chains per slab of keys
-STAGE_THREADS = int(os.environ.get("MCMCN_DIAG_THREADS", max(2, min(8, (os.cpu_count() or 4) // 2))))   # host threads staging a slab
+def _hostThreads(env):
+    """Host copy threads of this process: an even share of the cores among the ranks of this box, 2..8."""
+    share = (os.cpu_count() or 4) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    return int(os.environ.get(env, max(2, min(8, share // 2))))
+
+
+STAGE_THREADS = _hostThreads("MCMCN_DIAG_THREADS")
 
 
 def _rankWorld():
