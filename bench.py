@@ -436,6 +436,13 @@ def storeDiagnostics(gpu, store, chains):
     torch = gpu.torch
     from sampleDiagnosis import convergenceFromStore, orderStatisticsFromStore
     nKept = len(store.iterations)
+    if gpu.world > 1:
+        # warm the communicator up for both patterns (NCCL sets its peer-to-peer channels up at the first
+        # all-to-all: seconds, once per process), on a few columns and outside the timed region
+        few = store.tensor[:, :min(8 * gpu.world, store.tensor.shape[1])].contiguous()
+        convergenceFromStore(few, nKept, chains, group=gpu.group)
+        orderStatisticsFromStore(few, nKept, chains, group=gpu.group)
+        del few
     gpu.barrier()
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     info = {}
