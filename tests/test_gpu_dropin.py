@@ -183,6 +183,16 @@ def test_samplePosterior_loglikelihood_file_and_binary_store(tmp_path, monkeypat
     assert set(d.rhat) == set(keys)
 
 
+def test_tune_interval_beyond_the_16_bit_counters_is_refused():
+    from engine import Engine
+    meta, obj, prior = _regCase()
+    eng = Engine(parity.deviceObjective(obj, 10, "fp32"), 10, 10, "partial", 2)
+    eng.initialise(tuple(meta["parameterName"]), meta["startingPointValueRange"])
+    with pytest.raises(RuntimeError, match="16 bits"):
+        eng.run(0, 5, 3, 1, tuneInterval=70000)
+    eng.run(0, 5, 3, 1, tuneInterval=65535)
+
+
 def test_samplePosterior_argument_errors(tmp_path):
     import posteriorSampling as ps
     from objectives import Objective

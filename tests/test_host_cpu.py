@@ -452,3 +452,17 @@ def test_diagnostic_tables_and_stdout_text_from_given_statistics(capsys):
         assert capsys.readouterr().out in open(d + "/diagnose.stdout.txt").read()
         with pytest.raises(ValueError, match="Not both|no individual|no hyper"):
             diag.print(None, True, True)
+
+
+def test_fewer_chains_than_ranks_is_refused_on_every_rank_before_any_collective(monkeypatch, tmp_path):
+    """samplePosterior under torch.distributed: nChains < world must raise the same error on EVERY rank before
+    the first barrier (a rank-local error after it would leave the other ranks waiting forever)."""
+    import posteriorSampling as ps
+    from objectives import Objective
+    handle = Objective.linear_regression(numpy.ones((20, 1)), numpy.zeros(20))
+    for rank in range(4):
+        monkeypatch.setattr(ps, "_rankWorld", lambda rank=rank: (rank, 4))
+        monkeypatch.setattr(ps, "_barrier", lambda world: (_ for _ in ()).throw(AssertionError("collective reached")))
+        with pytest.raises(ValueError, match="fewer chains"):
+            ps.samplePosterior(3, 10, 5, ("b0", "sigma"), 2, 10, "partial", handle, str(tmp_path / "o"), displayProgress=False)
+    assert not os.path.exists(str(tmp_path / "o"))
