@@ -12,6 +12,7 @@ Reference symbols this module stands in for (``/root/reference/posteriorSampling
 import ctypes
 import os
 import math
+import threading
 
 import numpy
 import scipy.special
@@ -122,6 +123,7 @@ def _hostThreads(env):
 
 
 WRITER_THREADS = _hostThreads("MCMCN_STORE_THREADS")
+PREFAULT_THREADS = max(1, WRITER_THREADS // 2)
 
 
 def retainedCount(lo, hi, burn, thin):
@@ -153,6 +155,7 @@ class SampleStore(object):
         self.nRows = int(nRows)
         self.dtype = dtype
         self.iterations = []
+        self._stopPrefault = False
         self.path = path
         self.streamed = path is not None
         self.logLikSink = logLikSink
@@ -184,6 +187,32 @@ class SampleStore(object):
             npdt = numpy.float64 if dtype == torch.float64 else numpy.float32
             self.sink = numpy.lib.format.open_memmap(path, mode="w+", dtype=npdt,
                                                      shape=(self.nRows, engine.nCol, engine.nChains))
+            self._prefaulters = [threading.Thread(target=self._prefault, args=(k, PREFAULT_THREADS), daemon=True)
+                                 for k in range(PREFAULT_THREADS)]
+            for t in self._prefaulters:
+                t.start()
+
+    def _prefault(self, k, nThreads):
+        """Background thread k of nThreads: have the kernel allocate and map the file's pages (madvise
+        MADV_POPULATE_WRITE, Linux >= 5.14; through ctypes, which releases the GIL), 64 MB pieces in file
+        order dealt round-robin to the threads, while the chains burn in -- so that the row copies later
+        run at memory speed instead of one page fault per 4 KB.  Best effort: stops silently where the
+        call is not supported."""
+        try:
+            libc = ctypes.CDLL(None, use_errno=True)
+            page = os.sysconf("SC_PAGE_SIZE")
+            addr = self.sink.ctypes.data
+            lo = addr - addr % page
+            end = addr + self.sink.nbytes
+            step = 64 << 20
+            lo += k * step
+            while lo < end and not self._stopPrefault:
+                n = min(step, end - lo)
+                if libc.madvise(ctypes.c_void_p(lo), ctypes.c_size_t(n), 23) != 0:     # MADV_POPULATE_WRITE
+                    return
+                lo += nThreads * step
+        except Exception:
+            return
 
     # ---- what Engine.run needs
     def deviceRow(self):
@@ -262,6 +291,9 @@ class SampleStore(object):
             while self._pending:
                 self._retire(self._pending.pop(0))
             self._writers.shutdown()
+            self._stopPrefault = True
+            for t in self._prefaulters:
+                t.join()
             self.sink.flush()
         elif self.logLik is not None and self.logLikSink is not None:
             n = len(self.iterations)
