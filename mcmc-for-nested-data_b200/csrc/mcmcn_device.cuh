@@ -1211,44 +1211,58 @@ __global__ void __launch_bounds__(32 * NS) hyper_kernel(const HyperArgs a) {
 // (theta - c)^2, then  mean = c + S1 / G  and
 //   sum (theta - mu)^2 = (S2 - S1^2 / G) + G (mu - mean)^2     (two non-negative terms).
 // Agrees with the two-pass kernel to 1e-13 relative at C3's shape (tests/test_gpu_dropin.py).
-template <int NS>
-__global__ void __launch_bounds__(32 * NS) hyper_onepass_kernel(const HyperArgs a) {
-    __shared__ double red1[NS][33], red2[NS][33];
+// The sums are ALWAYS taken over MCMCN_HYPER_SLICES = 16 group slices (slice j = groups j, j + 16, ... in
+// order; then the 16 slices in order), whatever the launch shape, so that the result does not depend on how
+// many chains a GPU holds.  Shapes: CX chains per block row (a warp row reads CX * 8 contiguous bytes of one
+// group's values: 32 chains = 256 bytes per DRAM page touched measured 21.8 us at C3, 64 chains 19.1 us;
+// 16,384 chains: 284 / 238 / 205 us for 32 / 64 / 128) and SPR slices per thread row (16 / SPR rows).
+#define MCMCN_HYPER_SLICES 16
+template <int CX, int SPR>
+__global__ void __launch_bounds__(CX * (MCMCN_HYPER_SLICES / SPR)) hyper_onepass_kernel(const HyperArgs a) {
+    constexpr int NS = MCMCN_HYPER_SLICES;
+    __shared__ double red1[NS][CX + 1], red2[NS][CX + 1];
     const int tx = threadIdx.x, ty = threadIdx.y;
-    const int ch = blockIdx.x * 32 + tx;
+    const int ch = blockIdx.x * CX + tx;
     const int p = blockIdx.y;
     const bool on = ch < a.n_chains;
     const size_t S = (size_t)a.S;
     const double* th = a.theta + ((size_t)p * a.G) * S + ch;
     const double n = (double)a.G;
-    double c = 0.0, s1 = 0.0, s2 = 0.0;
+    double c = 0.0;
     if (on) {
         c = a.hyper[((size_t)0 * a.P + p) * S + ch];
         if (!finite64(c)) c = th[0];
-        // eight loads in flight per thread (a thread reads only G / NS values: without the unroll the
-        // loop is one L2 / DRAM latency per value); the sums keep their order
-        const double* tq = th + (size_t)ty * S;
-        const size_t step = (size_t)NS * S;
-        int g = ty;
-        for (; g + 7 * NS < a.G; g += 8 * NS, tq += 8 * step) {
-            double v[8];
+    }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = tq[(size_t)k * step];
+    for (int q = 0; q < SPR; ++q) {
+        const int slice = ty * SPR + q;
+        double s1 = 0.0, s2 = 0.0;
+        if (on) {
+            // eight loads in flight per thread and slice (a thread reads only G / 16 values per slice: without
+            // the unroll the loop is one L2 / DRAM latency per value); the sums keep their order
+            const double* tq = th + (size_t)slice * S;
+            const size_t step = (size_t)NS * S;
+            int g = slice;
+            for (; g + 7 * NS < a.G; g += 8 * NS, tq += 8 * step) {
+                double v[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const double d = v[k] - c;
+                for (int k = 0; k < 8; ++k) v[k] = tq[(size_t)k * step];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const double d = v[k] - c;
+                    s1 += d;
+                    s2 = fma(d, d, s2);
+                }
+            }
+            for (; g < a.G; g += NS, tq += step) {
+                const double d = *tq - c;
                 s1 += d;
                 s2 = fma(d, d, s2);
             }
         }
-        for (; g < a.G; g += NS, tq += step) {
-            const double d = *tq - c;
-            s1 += d;
-            s2 = fma(d, d, s2);
-        }
+        red1[slice][tx] = s1;
+        red2[slice][tx] = s2;
     }
-    red1[ty][tx] = s1;
-    red2[ty][tx] = s2;
     __syncthreads();
     if (ty == 0 && on) {
         double t1 = 0.0, t2 = 0.0;

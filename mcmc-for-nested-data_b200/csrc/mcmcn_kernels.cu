@@ -402,7 +402,16 @@ int mcmcn_run(const mcmcn_model* m, const mcmcn_state* s, const mcmcn_run_args* 
             const dim3 hg((unsigned)((s->n_chains + 31) / 32), (unsigned)m->n_params, 1);
             tic(1);
             if (m->n_groups >= 512 && !getenv("MCMCN_HYPER_TWO_PASS"))
-                hyper_onepass_kernel<32><<<hg, dim3(32, 32, 1), 0, stream>>>(h);   // 21 us at C3 (two passes: 24)
+            {
+                // the widest block row that still leaves about two blocks per SM (the sums do not depend on the shape)
+                const unsigned nc = (unsigned)s->n_chains, np = (unsigned)m->n_params;
+                if ((nc + 127) / 128 * np >= 296u)
+                    hyper_onepass_kernel<128, 2><<<dim3((nc + 127) / 128, np, 1), dim3(128, 8, 1), 0, stream>>>(h);
+                else if ((nc + 63) / 64 * np >= 144u)
+                    hyper_onepass_kernel<64, 1><<<dim3((nc + 63) / 64, np, 1), dim3(64, 16, 1), 0, stream>>>(h);
+                else
+                    hyper_onepass_kernel<32, 1><<<dim3((nc + 31) / 32, np, 1), dim3(32, 16, 1), 0, stream>>>(h);
+            }
             else if (m->n_groups >= 512) hyper_kernel<32><<<hg, dim3(32, 32, 1), 0, stream>>>(h);
             else if (m->n_groups >= 64) hyper_kernel<8><<<hg, dim3(32, 8, 1), 0, stream>>>(h);
             else hyper_kernel<1><<<hg, dim3(32, 1, 1), 0, stream>>>(h);

@@ -121,6 +121,30 @@ def test_production_kernels_with_many_groups_equal_general_bit_for_bit(monkeypat
     _assertIdentical(prod, gen)
 
 
+def test_results_do_not_depend_on_how_many_chains_share_the_gpu():
+    """Philox and the start-state streams are keyed by the global chain id, and every sum over groups is taken
+    in a fixed order whatever the launch shape (the one-pass Gibbs kernel picks its block shape from the chain
+    count: 32, 64 or 128 chains per block row), so chains 0..63 come out bit-identical whether they run alone
+    or next to 9,408 others -- the property that makes a run independent of the number of GPUs."""
+    import torch
+    from engine import Engine
+    G, R, K = 520, 12, 3
+    obj, names, nResp, ranges = parity.syntheticRegression(G=G, R=R, K=K)
+    out = []
+    for nC in (64, 4736, 9472):                        # hyper_onepass_kernel<32,1>, <64,1>, <128,2>
+        eng = Engine(parity.deviceObjective(obj, nResp, "fp32"), G, nResp, "partial", nC, chainId0=0, seed=11)
+        eng.initialise(names, ranges)
+        eng.run(0, 130, 110, 2)
+        torch.cuda.synchronize()
+        st = eng.getState()
+        out.append(dict((k, v[..., :64].copy()) for k, v in st.items()))
+        del eng
+        torch.cuda.empty_cache()
+    for other in out[1:]:
+        for key in ("theta", "ll", "scale", "mu", "sigma2"):
+            numpy.testing.assert_array_equal(out[0][key], other[key], err_msg=key)
+
+
 # ------------------------------------------------------------------ 2. one-pass Gibbs kernel vs the oracle
 @pytest.mark.parametrize("precision,tol", [("fp64", 1e-11), ("fp32", 1e-5)])
 def test_replay_with_512_groups_meets_the_one_pass_hyper_kernel(precision, tol, monkeypatch):
