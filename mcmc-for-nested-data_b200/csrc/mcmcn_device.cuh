@@ -729,6 +729,19 @@ struct SweepArgs {
     int tc_stages;                // 2: the next group's block is staged while this one is used; 1: big blocks
 };
 
+// Arguments of eval_tc_kernel (mcmcn_tc.cuh): the log-likelihood of one candidate vector per chain over a
+// range of (small) groups on the tensor core -- complete pooling split over observations.
+struct EvalTcArgs {
+    const void* tc_data;          // operand blocks of the small groups (mcmcn_model.tc_data of the split model)
+    const long long* tc_group_off;
+    const int* group_nobs;
+    const double* bbar;           // [K] common reference point of every small group (row 0 of the split model's obj_const)
+    const double* cand;           // [P][S] candidate vector per chain
+    double* part;                 // [gridDim.x][S] log-likelihood of the candidate over the CTA's group range
+    int P, G, n_chains, S;
+    int tc_stage_bytes;
+};
+
 // Compile-time specialisation of the step kernel.  F < 0: everything decided at run time (the
 // general kernel: replay tapes, traces, groups streamed through the tile).  F >= 0: the
 // production variants -- no tape, no trace, every task fits the tile -- with the pooling mode
@@ -1309,6 +1322,8 @@ struct CompleteArgs {
     unsigned long long seed;
     int tune, count;
     mcmcn_prior prior;            // of name p
+    mcmcn_prior prior_next;       // of name p + 1 (decide kernel with propose_next)
+    int propose_next;             // complete_decide_kernel also forms the proposal and candidate of name p + 1
     double* theta;                // [P][1][S]
     double* scale;
     unsigned* counts;
@@ -1326,27 +1341,33 @@ struct CompleteArgs {
     unsigned char* tr_acc;
 };
 
-static __global__ void __launch_bounds__(128) complete_propose_kernel(const CompleteArgs a) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.S) return;
+// Proposal of name p for chain c (lanes past the last chain redo its work): candidate vector, parked proposal,
+// uniform and proposal log-prior.
+__device__ __forceinline__ void complete_propose(const CompleteArgs& a, int p, const mcmcn_prior& prior, int c) {
     const int chl = min(c, a.n_chains - 1);
-    const size_t S = (size_t)a.S, at = (size_t)a.p * S + chl;
+    const size_t S = (size_t)a.S, at = (size_t)p * S + chl;
     double z, u;
     if (a.tape_z) {
         z = a.tape_z[at];
         u = a.tape_u[at];
     } else {                      // the step kernels' recipe with G = 1: one Philox call per two sweeps
-        const uint4 rnd = philox_draw(a.chain_id0 + chl, a.seed, a.iter, MCMCN_STREAM_SWEEP, (unsigned)(a.p >> 1), 1u);
+        const uint4 rnd = philox_draw(a.chain_id0 + chl, a.seed, a.iter, MCMCN_STREAM_SWEEP, (unsigned)(p >> 1), 1u);
         float zc, zs;
         normal_pair_from(rnd.x, rnd.y, zc, zs);
-        z = (double)((a.p & 1) ? zs : zc);
-        u = uniform_from32((a.p & 1) ? rnd.w : rnd.z);
+        z = (double)((p & 1) ? zs : zc);
+        u = uniform_from32((p & 1) ? rnd.w : rnd.z);
     }
     const double prop = __dadd_rn(a.theta[at], __dmul_rn(a.scale[at], z));   // :304-306
-    for (int k = 0; k < a.P; ++k) a.cand[(size_t)k * S + c] = (k == a.p) ? prop : a.theta[(size_t)k * S + chl];
+    for (int k = 0; k < a.P; ++k) a.cand[(size_t)k * S + c] = (k == p) ? prop : a.theta[(size_t)k * S + chl];
     a.park[c] = prop;
     a.park[S + c] = u;
-    a.park[2 * S + c] = prior_logpdf(a.prior, prop);
+    a.park[2 * S + c] = prior_logpdf(prior, prop);
+}
+
+static __global__ void __launch_bounds__(128) complete_propose_kernel(const CompleteArgs a) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.S) return;
+    complete_propose(a, a.p, a.prior, c);
 }
 
 // block = (32 chains, 32 slices of the small groups): slice sums in group order, then the 32 slice
@@ -1364,7 +1385,11 @@ static __global__ void __launch_bounds__(1024) complete_decide_kernel(const Comp
         slice_sum[threadIdx.y][threadIdx.x] = sum;
     }
     __syncthreads();
-    if (threadIdx.y != 0 || c >= a.n_chains) return;
+    if (threadIdx.y != 0) return;
+    if (c >= a.n_chains) {                                              // padding lanes only keep the next candidate filled
+        if (a.propose_next) complete_propose(a, a.p + 1, a.prior_next, c);
+        return;
+    }
     const size_t at = (size_t)a.p * S + c;
     double llp = 0.0;
 #pragma unroll
@@ -1414,6 +1439,8 @@ static __global__ void __launch_bounds__(1024) complete_decide_kernel(const Comp
         }
         a.counts[at] = cnt;
     }
+    // the next sweep's proposal in the same launch (this chain's own state only; tapes are indexed by name)
+    if (a.propose_next) complete_propose(a, a.p + 1, a.prior_next, c);
 }
 
 // ---------------------------------------------------------------- retained-sample write-back

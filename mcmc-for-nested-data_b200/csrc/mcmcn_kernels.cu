@@ -233,10 +233,33 @@ static int run_complete_split(const mcmcn_model* m, const mcmcn_state* s, const 
     const sweep_fn efn = g.wide ? ks->eval_wide : ks->eval_one;
     rc = set_smem_attr((const void*)efn, g.tile_bytes);
     if (rc) return rc;
+    // linear regression with FP32 observation math: the evaluation runs on the tensor core (eval_tc_kernel),
+    // one partial log-likelihood per group RANGE instead of one per small group
+    const bool etc = tc_eligible(e);
+    EvalTcArgs ta;
+    memset(&ta, 0, sizeof(ta));
+    Geometry tg = g;
+    eval_tc_fn tfn = nullptr;
+    if (etc) {
+        int sb = 0, st = 0;
+        tg = tc_geometry(e, s->n_chains, &sb, &st);
+        if (st < 2) tg.smem = tg.tile_bytes = (size_t)2 * sb + 4096 + 1024;     // the kernel double-buffers whatever the block size
+        ta.tc_data = e->tc_data;
+        ta.tc_group_off = reinterpret_cast<const long long*>(e->tc_group_off);
+        ta.group_nobs = e->group_nobs;
+        ta.bbar = e->obj_const;
+        ta.cand = cand;
+        ta.part = part;
+        ta.P = P; ta.G = e->n_groups; ta.n_chains = s->n_chains; ta.S = S;
+        ta.tc_stage_bytes = sb;
+        tfn = tc_eval_kernel(e->n_coef > 8 ? 2 : 1);
+        rc = set_smem_attr((const void*)tfn, tg.smem);
+        if (rc) return rc;
+    }
 
     CompleteArgs c;
     memset(&c, 0, sizeof(c));
-    c.P = P; c.n_chains = s->n_chains; c.S = S; c.n_parts = e->n_groups;
+    c.P = P; c.n_chains = s->n_chains; c.S = S; c.n_parts = etc ? (int)tg.grid.x : e->n_groups;
     c.chain_id0 = s->chain_id0; c.seed = r->seed;
     c.theta = s->theta; c.scale = s->scale; c.counts = s->counts; c.ll = s->ll; c.lprior = s->lprior;
     c.cand = cand; c.part = part; c.park = park;
@@ -261,9 +284,16 @@ static int run_complete_split(const mcmcn_model* m, const mcmcn_state* s, const 
         for (int p = 0; p < P; ++p) {                                   // StepMethod.step, :594-597
             c.p = p;
             c.prior = m->prior[p];
-            complete_propose_kernel<<<nb, 128, 0, stream>>>(c);
+            if (p == 0) complete_propose_kernel<<<nb, 128, 0, stream>>>(c);       // later names: proposed by the decide launch before
             if (r->timing) r->timing[3] += 1.0;
-            CK(launch_sweep(efn, g.grid, g.block, g.tile_bytes, stream, ea));
+            if (etc) {
+                void* args[] = {&ta};
+                CK(cudaLaunchKernel((const void*)tfn, tg.grid, tg.block, args, tg.smem, stream));
+            } else {
+                CK(launch_sweep(efn, g.grid, g.block, g.tile_bytes, stream, ea));
+            }
+            c.propose_next = p + 1 < P ? 1 : 0;
+            c.prior_next = m->prior[p + 1 < P ? p + 1 : p];
             complete_decide_kernel<<<(unsigned)(S / 32), dim3(32, 32, 1), 0, stream>>>(c);
         }
         if (r->store && i >= r->burn && (i % r->thin) == 0) {

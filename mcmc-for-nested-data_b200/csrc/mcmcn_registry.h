@@ -42,5 +42,8 @@ const KernelSet* sets_logit(int* n);
 const KernelSet* sets_gauss(int* n);
 sweep_fn tc_sweep_kernel(int f, bool uniform208, int k_blocks);    // mcmcn_sets_tc.cu (one K block), mcmcn_sets_tc2.cu (two)
 sweep_fn tc_sweep_kernel_two_blocks(int f);
+typedef void (*eval_tc_fn)(const EvalTcArgs);
+eval_tc_fn tc_eval_kernel(int k_blocks);             // eval_tc_kernel<1> (mcmcn_sets_tc.cu), <2> (mcmcn_sets_tc2.cu)
+eval_tc_fn tc_eval_kernel_two_blocks();
 
 }  // namespace mcmcn

@@ -24,4 +24,5 @@ sweep_fn tc_sweep_kernel(int f, bool uniform208, int k_blocks) {
         default: return sweep_tc_kernel<-1, false>;
     }
 }
+eval_tc_fn tc_eval_kernel(int k_blocks) { return k_blocks == 2 ? tc_eval_kernel_two_blocks() : eval_tc_kernel<1>; }
 }  // namespace mcmcn

@@ -13,4 +13,5 @@ sweep_fn tc_sweep_kernel_two_blocks(int f) {
         default: return sweep_tc_kernel<-1, false, 2>;
     }
 }
+eval_tc_fn tc_eval_kernel_two_blocks() { return eval_tc_kernel<2>; }
 }  // namespace mcmcn

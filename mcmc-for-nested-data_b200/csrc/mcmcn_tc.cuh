@@ -563,4 +563,117 @@ __global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) sweep_tc_kernel(const Swe
     if (warp == 0) tmem_free(tbase, MCMCN_TC_COLS);
 }
 
+// ---------------------------------------------------------------- complete pooling: evaluation on the tensor core
+// Complete pooling split over observations (mcmcn_model.split; CompletePooling, posteriorSampling.py:662-685):
+// every chain evaluates ONE candidate vector over all N observations, handed over as many small groups.
+// The candidate does not depend on the group, and the small groups share one reference point (the pooled
+// least-squares fit), so the A operand -- the chain's centred coefficients, split hi / lo -- is written to
+// tensor memory once per CTA; then per group: TMA stage, 3 KB + 1 MMAs per chunk, read-back of the chain's
+// own row of residuals, sum of squares (FP32 pairs folded into FP64 per chunk).  The sum of squares of the
+// CTA's whole group range is finished once: part[range][chain] = S m - N_range (log sigma + log sqrt(2 pi)).
+// grid = (group ranges, chain blocks of 128); block = 128 threads; 128 TMEM columns -> four CTAs per SM.
+template <int KB>
+__global__ void __launch_bounds__(MCMCN_TC_THREADS, 4) eval_tc_kernel(const EvalTcArgs a) {
+    typedef TcMap<KB> M;
+    constexpr int CH = M::CH;
+    const int K = a.P - 1;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ unsigned long long mbar_s[3];          // [0..1] TMA stage full, [2] accumulator full
+    __shared__ unsigned tmem_base_s;
+
+    const int nr = gridDim.x;
+    const int g0 = (int)(((long long)a.G * blockIdx.x) / nr), g1 = (int)(((long long)a.G * (blockIdx.x + 1)) / nr);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const unsigned ones = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const unsigned stage0 = ones + MCMCN_TC_ONES_BYTES;
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&mbar_s[i]), 1);
+    }
+    {   // constant A operand of the ne MMA: every row (1, 1, 1, 0 | 0, 0, 0, 0), K-major core matrices
+        for (int i = tid; i < MCMCN_TC_ONES_BYTES / 16; i += MCMCN_TC_THREADS) {
+            const float one = ((i >> 3) & 1) == 0 ? 1.0f : 0.0f;      // 8 rows x 16 bytes per K half
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ones + 16u * i), "f"(one), "f"(one), "f"(one), "f"(0.0f) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_s, MCMCN_TC_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tbase = tmem_base_s;
+    const unsigned tlane = tbase + ((unsigned)warp << 21);
+    unsigned mb_tma0 = smem_u32(&mbar_s[0]), mb_mma = smem_u32(&mbar_s[2]);
+    asm volatile("" : "+r"(mb_tma0), "+r"(mb_mma));
+
+    const float* tc = reinterpret_cast<const float*>(a.tc_data);
+    auto stage_group = [&](int s, int g) {                             // thread 0 only
+        const long long e0 = a.tc_group_off[g], e1 = a.tc_group_off[g + 1];
+        const unsigned bytes = (unsigned)((e1 - e0) * 4);
+        MCMCN_CHECK(s >= 0 && s < 2 && g >= g0 && g < g1);
+        MCMCN_CHECK(bytes > 0 && (bytes & 15u) == 0u && (int)bytes <= a.tc_stage_bytes && ((e0 * 4) & 15) == 0);
+        mbar_expect_tx(mb_tma0 + 8u * s, bytes);
+        tma_bulk_g2s(stage0 + (unsigned)s * (unsigned)a.tc_stage_bytes, tc + e0, bytes, mb_tma0 + 8u * s);
+    };
+    if (tid == 0 && g0 < g1) {
+        stage_group(0, g0);
+        if (g0 + 1 < g1) stage_group(1, g0 + 1);
+    }
+
+    const int ch = blockIdx.y * MCMCN_TC_THREADS + tid;
+    const bool on = ch < a.n_chains;
+    const int chl = min(ch, a.n_chains - 1);
+    const size_t S = (size_t)a.S;
+    {   // A operand: the candidate's centred coefficients (FP32), split hi / lo, 8 columns per K block
+        const double* ck = a.cand + chl;
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+            unsigned hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = 8 * kb + j;
+                const float b = k < K ? (float)__dsub_rn(ck[(size_t)k * S], a.bbar[k]) : 0.0f;
+                hi[j] = tf32_rn(b);
+                lo[j] = tf32_rn(b - __uint_as_float(hi[j]));
+            }
+            tmem_st8(tlane + M::A_HI + 8 * kb, hi);
+            tmem_st8(tlane + M::A_LO + 8 * kb, lo);
+        }
+    }
+    double aux_m, aux_r1;                                              // -1/(2 sigma^2); log sigma + log sqrt(2 pi) (per observation)
+    tc_sigma_terms(a.cand[(size_t)K * S + chl], 1, aux_m, aux_r1);
+    tmem_wait_st();
+
+    unsigned tma_phase = 0, mma_phase = 0;
+    double acc = 0.0;
+    long long nobs = 0;
+    for (int g = g0; g < g1; ++g) {
+        const int s = (g - g0) & 1;
+        const int R = a.group_nobs[g];
+        const int np = max(16, (R + 15) & ~15);
+        const int nchunks = (np + CH - 1) / CH;
+        const unsigned stage = stage0 + (unsigned)s * (unsigned)a.tc_stage_bytes;
+        MCMCN_CHECK(np * 32 * (2 * KB + 1) == (int)((a.tc_group_off[g + 1] - a.tc_group_off[g]) * 4));
+        nobs += R;
+        mbar_wait(mb_tma0 + 8u * s, (tma_phase >> s) & 1u);
+        tma_phase ^= 1u << s;
+        for (int c = 0; c < nchunks; ++c) {
+            // every lane has read the accumulator of the chunk before (and, the first time, written its A operand)
+            if (tc_rendezvous_issuer()) tc_issue_chunk<KB>(tbase, stage, ones, np, c, mb_mma);
+            mbar_wait(mb_mma, mma_phase);
+            mma_phase ^= 1u;
+            tc_fence_after();
+            const int nc = min(CH, np - c * CH);
+            acc += tc_sum_squares(tlane + MCMCN_TC_D, nc >> 4);
+        }
+        // every MMA that read this stage has completed (all threads waited on its mbarrier)
+        if (tid == 0 && g + 2 < g1) stage_group(s, g + 2);
+    }
+    if (on) a.part[(size_t)blockIdx.x * S + ch] = acc * aux_m - (double)nobs * aux_r1;
+    tmem_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_free(tbase, MCMCN_TC_COLS);
+}
+
 }  // namespace mcmcn

@@ -382,19 +382,25 @@ class Engine(object):
         self._split = None
         if pooling == "complete" and self.nObservations >= splitMinObservations:
             N = self.nObservations
-            parts = [128] * (N // 128) + ([N % 128] if N % 128 else [])
-            sm, skeep = self._buildModel(parts, pooling, taskObsTarget, tensorCore=False)
+            # one accumulator chunk of the tcgen05 evaluation kernel per small group (112 observations for
+            # K <= 8, 96 for K = 9..16); every small group centred on the pooled least-squares fit
+            size = 128
+            if objective.kind == nat.OBJ_LINEAR_REGRESSION and objective.precision == "fp32":
+                size = 112 if objective.nCoef <= 8 else 96
+            parts = [size] * (N // size) + ([N % size] if N % size else [])
+            sm, skeep = self._buildModel(parts, pooling, taskObsTarget, tensorCore=True, commonReference=True)
             scratch = torch.zeros(((P + len(parts) + 3) * S,), dtype=f64, device=dev)
             self._split = (sm, skeep, scratch)
             self.model.split = ctypes.addressof(sm)
             self.model.split_scratch = _ptr(scratch)
 
-    def _buildModel(self, stepped, pooling, taskObsTarget, tensorCore):
+    def _buildModel(self, stepped, pooling, taskObsTarget, tensorCore, commonReference=False):
         """Pack the objective's observations as the groups `stepped` and describe them as a
         mcmcn_model (include/mcmcn.h).  Returns the model and the tensors / arrays it points into."""
         objective, dev = self.objective, self.device
         nG = len(stepped)
-        data, group_off, group_nobs, obj_const = objective.pack(stepped)
+        data, group_off, group_nobs, obj_const = objective.pack(stepped, commonReference) \
+            if commonReference else objective.pack(stepped)
         elem = data.dtype.itemsize
         cap = self.lib.mcmcn_tile_capacity_bytes() // elem
         task_group0 = [0]

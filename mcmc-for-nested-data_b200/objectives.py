@@ -124,10 +124,14 @@ class Objective(object):
     def elementDtype(self):
         return numpy.float32 if self.precision == "fp32" else numpy.float64
 
-    def pack(self, nResponsesPerGroup):
+    def pack(self, nResponsesPerGroup, commonReference=False):
         """Pack the observation data into one block per *stepped* group (include/mcmcn.h,
         mcmcn_model).  ``nResponsesPerGroup`` is the list the step method uses (a single
         entry under complete pooling, posteriorSampling.py:667-671).
+        ``commonReference`` (linear regression): every group is centred on the SAME reference point,
+        the least-squares fit over all observations, instead of its own fit -- what complete pooling
+        split over observations wants: the chain's one candidate vector then has one centred form for
+        every small group.
         Returns (data, group_off[G+1], group_nobs[G], obj_const or None)."""
         nResp = [int(r) for r in nResponsesPerGroup]
         if sum(nResp) != self.nObservations:
@@ -169,6 +173,7 @@ class Objective(object):
         start = 0
         if self.kind == nat.OBJ_LINEAR_REGRESSION:
             bbar = numpy.zeros((len(nResp), self.nCoef), dtype=numpy.float64)
+            pooledFit = numpy.linalg.lstsq(self.X, self.y, rcond=None)[0] if commonReference else None
         for g, r in enumerate(nResp):
             q = nquads[g]
             blk = data[group_off[g]:group_off[g + 1]].reshape(q, unit)
@@ -177,7 +182,10 @@ class Objective(object):
                 # centre the group on its least-squares fit (FP32 conditioning, see LinReg in
                 # csrc/mcmcn_device.cuh): store ne = X.bbar - y, keep bbar in FP64
                 Xg, yg = self.X[rows], self.y[rows]
-                bbar[g] = numpy.linalg.lstsq(Xg, yg, rcond=None)[0] if r > 0 else 0.0
+                if pooledFit is not None:
+                    bbar[g] = pooledFit
+                else:
+                    bbar[g] = numpy.linalg.lstsq(Xg, yg, rcond=None)[0] if r > 0 else 0.0
                 xs = numpy.zeros((q * 4, KP), dtype=dt)
                 xs[:r, :K] = Xg
                 ys = numpy.zeros(q * 4, dtype=dt)

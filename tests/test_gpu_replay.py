@@ -275,19 +275,25 @@ def test_replay_bernoulli_logit(pooling):
     assert ties64 == 0
 
 
-@pytest.mark.parametrize("objective", ["regression", "logit"])
-def test_replay_complete_pooling_split_over_observations(objective):
+@pytest.mark.parametrize("objective", ["regression", "regression-8", "regression-12", "regression-fp32-pipe", "logit"])
+def test_replay_complete_pooling_split_over_observations(objective, monkeypatch):
     """Complete pooling at scale: the engine evaluates the single group of all N observations as
-    groups of 128 in parallel (mcmcn_model.split: propose / eval / decide kernels) -- same tape
-    replay criteria as the step kernels; N = 5,000 leaves a last group of 8 observations."""
-    if objective == "regression":
-        obj, names, nResp, ranges = parity.syntheticRegression(G=50, R=100, K=2)
-        prior = [scipy.stats.norm(0, 10), scipy.stats.norm(0, 10), scipy.stats.gamma(2)]
+    small groups in parallel (mcmcn_model.split: propose / eval / decide kernels, the next proposal
+    formed by the decide launch) -- same tape replay criteria as the step kernels.  Linear regression
+    with FP32 observation math evaluates on the tensor core (eval_tc_kernel: groups of 112 observations,
+    96 for K > 8, all centred on the pooled least-squares fit), everything else with the FP32-pipe
+    eval_kernel over groups of 128; N = 5,000 leaves a short last group."""
+    if objective.startswith("regression"):
+        K = {"regression": 2, "regression-8": 8, "regression-12": 12, "regression-fp32-pipe": 2}[objective]
+        if objective == "regression-fp32-pipe":
+            monkeypatch.setenv("MCMCN_NO_TC", "1")
+        obj, names, nResp, ranges = parity.syntheticRegression(G=50, R=100, K=K)
+        prior = [scipy.stats.norm(0, 10)] * K + [scipy.stats.gamma(2)]
     else:
         obj, names, nResp, ranges = parity.syntheticLogit(G=50, R=100)
         prior = [scipy.stats.norm(0, 5), scipy.stats.cauchy(0, 5)]
-    res = parity.replay(obj, names, 50, nResp, "complete", prior, ranges, nChains=37, nIter=60,
-                        nSamples=20, precision="fp32")
+    res = parity.replay(obj, names, 50, nResp, "complete", prior, ranges, nChains=37 if objective != "regression-8" else 150,
+                        nIter=60, nSamples=20, precision="fp32")
     assert res.engine.model.split
     err, ties = parity.checkReplay(res, 1e-5, 1e-5)
     numpy.testing.assert_allclose(res.rows, res.oracleRows, rtol=1e-9, atol=1e-9)

@@ -16,9 +16,12 @@ from objectives import Objective  # noqa: E402
 nIter = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 X, y, names, ranges = bench.makeWorkload(1024, 200, 8)
 prior = [scipy.stats.norm(0, 10)] * 8 + [scipy.stats.gamma(2)]
-for label, env, n in (("split over observations", None, nIter), ("single group, one warp per 128 chains", "1", 2)):
+for label, env, n in (("split over observations, tcgen05 evaluation", None, nIter),
+                      ("split over observations, FP32-pipe evaluation", "MCMCN_NO_TC", nIter),
+                      ("single group, one warp per 128 chains", "MCMCN_NO_SPLIT", 2)):
+    os.environ.pop("MCMCN_NO_TC", None)
     if env:
-        os.environ["MCMCN_NO_SPLIT"] = env
+        os.environ[env] = "1"
     eng = Engine(Objective.linear_regression(X, y, "fp32"), 1024, 200, "complete", 1024, priorDistribution=prior, seed=1)
     eng.initialise(names, ranges)
     eng.run(0, 2, 1000, 1)
