@@ -283,22 +283,26 @@ def test_replay_complete_pooling_split_over_observations(objective, monkeypatch)
     with FP32 observation math evaluates on the tensor core (eval_tc_kernel: groups of 112 observations,
     96 for K > 8, all centred on the pooled least-squares fit), everything else with the FP32-pipe
     eval_kernel over groups of 128; N = 5,000 leaves a short last group."""
-    if objective.startswith("regression"):
-        K = {"regression": 2, "regression-8": 8, "regression-12": 12, "regression-fp32-pipe": 2}[objective]
+    # (coefficients, groups x observations of the data, chains, iterations, retained): the oracle runs chain by
+    # chain, so the wide case (two 128-chain blocks) is short
+    K, G, R, nC, nIter, nSamples = {"regression": (2, 50, 100, 37, 60, 20), "regression-8": (8, 20, 110, 130, 12, 6),
+                                    "regression-12": (12, 20, 110, 9, 30, 10), "regression-fp32-pipe": (2, 50, 100, 5, 40, 20),
+                                    "logit": (0, 50, 100, 37, 60, 20)}[objective]
+    if K:
         if objective == "regression-fp32-pipe":
             monkeypatch.setenv("MCMCN_NO_TC", "1")
-        obj, names, nResp, ranges = parity.syntheticRegression(G=50, R=100, K=K)
+        obj, names, nResp, ranges = parity.syntheticRegression(G=G, R=R, K=K)
         prior = [scipy.stats.norm(0, 10)] * K + [scipy.stats.gamma(2)]
     else:
-        obj, names, nResp, ranges = parity.syntheticLogit(G=50, R=100)
+        obj, names, nResp, ranges = parity.syntheticLogit(G=G, R=R)
         prior = [scipy.stats.norm(0, 5), scipy.stats.cauchy(0, 5)]
-    res = parity.replay(obj, names, 50, nResp, "complete", prior, ranges, nChains=37 if objective != "regression-8" else 150,
-                        nIter=60, nSamples=20, precision="fp32")
+    res = parity.replay(obj, names, G, nResp, "complete", prior, ranges, nChains=nC, nIter=nIter,
+                        nSamples=nSamples, precision="fp32")
     assert res.engine.model.split
     err, ties = parity.checkReplay(res, 1e-5, 1e-5)
     numpy.testing.assert_allclose(res.rows, res.oracleRows, rtol=1e-9, atol=1e-9)
-    res = parity.replay(obj, names, 50, nResp, "complete", prior, ranges, nChains=3, nIter=60,
-                        nSamples=20, precision="fp64", force=False)
+    res = parity.replay(obj, names, G, nResp, "complete", prior, ranges, nChains=3, nIter=nIter,
+                        nSamples=nSamples, precision="fp64", force=False)
     err, ties = parity.checkReplay(res, 1e-11, 0.0)
     assert ties == 0
     numpy.testing.assert_allclose(res.rows, res.oracleRows, rtol=1e-9, atol=1e-9)
