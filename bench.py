@@ -475,7 +475,31 @@ def fullRun(gpu, args, chainsTotal, nIter, nSamples, withDiagnostics):
     from objectives import Objective
     G, R, K = args.groups, args.obs, args.coef
     X, y, names, ranges = makeWorkload(G, R, K)                       # host numpy arrays: what a user holds
-    base = args.output_root or ("/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir())
+    # where the store goes: the first of /dev/shm, the temp directory, gpurun_out/ with room for it; if none has,
+    # fewer retained rows (said in the record) rather than a failed run
+    elem = 8 if args.store_dtype == "float64" else 4
+    rowBytes = (K + 1) * (G + 2) * chainsTotal * elem
+    need = nSamples * rowBytes
+    roots = [args.output_root] if args.output_root else ["/dev/shm", tempfile.gettempdir(), os.path.join(ROOT, "gpurun_out")]
+    free = []
+    for cand in roots:
+        try:
+            os.makedirs(cand, exist_ok=True)
+            free.append((shutil.disk_usage(cand).free, cand))
+        except OSError:
+            continue
+    fits = [c for f, c in free if f >= 1.05 * need + (1 << 30)]
+    reduced = None
+    if fits:
+        base = fits[0]
+    else:
+        room, base = max(free) if free else (0, tempfile.gettempdir())
+        reduced = max(4, int(0.8 * room // max(rowBytes, 1)) // 2 * 2)
+        nSamples = min(nSamples, reduced)
+    if gpu.world > 1:                                   # one decision for all ranks (rank 0's)
+        choice = [base, nSamples, reduced]
+        gpu.dist.broadcast_object_list(choice, src=0)
+        base, nSamples, reduced = choice
     out = os.path.join(base, "mcmcn_bench_%s" % (os.environ.get("MASTER_PORT", "0") if gpu.world > 1 else os.getpid()))
     ps.CSV_VALUE_LIMIT = 0                                             # binary store
     ps.STORE_DTYPE = args.store_dtype
@@ -489,7 +513,6 @@ def fullRun(gpu, args, chainsTotal, nIter, nSamples, withDiagnostics):
     run = ps.lastRun
     eng, store = run["engine"], run["store"]
     rows = len(run["retained"])
-    elem = 8 if args.store_dtype == "float64" else 4
     myChains = run["chains"][1] - run["chains"][0]
     d2h = rows * eng.nCol * eng.S * elem
     h2d = int(eng.stepInput.numel() * eng.stepInput.element_size() + eng._data.numel() * eng._data.element_size()
@@ -503,6 +526,8 @@ def fullRun(gpu, args, chainsTotal, nIter, nSamples, withDiagnostics):
                      "directory": base, "device_ring_bytes": int(run["store_device_bytes"]),
                      "pinned_host_bytes": int(run["store_device_bytes"])},
            "h2d_bytes": h2d, "d2h_bytes": int(d2h)}
+    if reduced is not None:
+        rec["store"]["note"] = "nSamples cut to %d: no directory with room for the configured store" % nSamples
     del eng, store
     ps.lastRun = None
     torch.cuda.empty_cache()
@@ -555,11 +580,18 @@ def runGpu(args):
             "clocks": main["clocks"], "diagnostics": main.get("diagnostics")}
 
     # ---- e2e: the configuration through samplePosterior, host arrays in, sample files out
+    full = None
     if args.coef and not args.no_full_run:
-        if world == 1:
-            full = fullRun(gpu, args, chains, args.full_iters, args.full_samples, withDiagnostics=True)
-        else:
-            full = fullRun(gpu, args, C4_CHAINS, args.c4_iters, args.c4_samples, withDiagnostics=True)
+        try:
+            if world == 1:
+                full = fullRun(gpu, args, chains, args.full_iters, args.full_samples, withDiagnostics=True)
+            else:
+                full = fullRun(gpu, args, C4_CHAINS, args.c4_iters, args.c4_samples, withDiagnostics=True)
+        except Exception as err:                        # the line is still printed, with the failure in it
+            import traceback
+            traceback.print_exc()
+            line["full_run"] = {"error": "%s: %s" % (type(err).__name__, err)}
+    if full is not None:
         stepsEq = full["iterations"] / float(args.iters_per_step)
         line["e2e"] = {"value": full["chain_iterations_per_s"], "unit": UNIT,
                        "h2d_bytes_per_step": int(full["h2d_bytes"] / stepsEq), "d2h_bytes_per_step": int(full["d2h_bytes"] / stepsEq),
@@ -570,10 +602,11 @@ def runGpu(args):
         line["full_run"] = full
     else:
         line["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                       "what": "skipped (--no-full-run)"}
+                       "what": "skipped (--no-full-run)" if args.no_full_run or not args.coef else "failed, see full_run.error"}
 
     # ---- sub-records (one GPU): config 4's single-GPU point and config 5
     if world == 1 and args.workload == "c3" and not args.no_sub_records:
+      try:
         sub = argparse.Namespace(**vars(args))
         sub.steps, sub.warmup = 5, 3
         c4 = stepPass(gpu, sub, C4_CHAINS, 0, withClocks=False, diagnostics=True)
@@ -589,10 +622,17 @@ def runGpu(args):
             line["c5_" + pooling] = {"workload": workloadConfig(c5, 4096)["workload"], "chains": 4096, "value": v5, "unit": UNIT,
                                      "evals_per_sec": v5 * 2 * 500000, "steps": c5.steps, "warmup": c5.warmup,
                                      "iters_per_step": c5.iters_per_step, "kernel_ms": r5["kernel_ms"], "roofline": r5["roofline"]}
+      except Exception as err:
+        import traceback
+        traceback.print_exc()
+        line["sub_records_error"] = "%s: %s" % (type(err).__name__, err)
 
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpuBaselineRecord(args)
+            try:
+                line["cpu_baseline"] = cpuBaselineRecord(args)
+            except Exception as err:
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "failed: %s" % err}
         emit(json.dumps(line))
     if world > 1:
         gpu.dist.destroy_process_group()
