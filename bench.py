@@ -287,14 +287,15 @@ def roofline(args, tensorCore, sweepMs, chains, peakFp32, peakTf32, peakMufu):
     G, R, K = args.groups, args.obs, args.coef
     scale = chains / 1024.0
     if K == 0:
-        # C5.  The kernel executes one ex2 per evaluation and one lg2 per 16 (logarithm of the product of 16
-        # factors): 1.0625 MUFU per evaluation -> `achieved` / `frac` are that EXECUTED rate over the
-        # measured MUFU peak.  SURVEY.md section 8d's algorithmic figure (2 MUFU per evaluation: ex2 + lg2)
+        # C5.  The kernel executes one ex2 per evaluation and one lg2 per fold of up to 64 observations (logarithm
+        # of the product of the factors): with 50 trials per group 1 + 1/50 = 1.02 MUFU per evaluation ->
+        # `achieved` / `frac` are that EXECUTED rate over the measured MUFU peak.  SURVEY.md section 8d's algorithmic figure (2 MUFU per evaluation: ex2 + lg2)
         # is reported beside it as `frac_at_survey_2_mufu_per_eval`.
         evals = 2.0 * G * R * chains
-        executed = 1.0625 * evals / (sweepMs * 1e-3)
+        perEval = 1.0 + float(-(-R // 64)) / R                      # one ex2 per observation, one lg2 per fold of 64
+        executed = perEval * evals / (sweepMs * 1e-3)
         return {"bound": "mufu", "kernel": "sweep_kernel<Logit,4,float>", "achieved": executed / 1e9, "peak": peakMufu / 1e9,
-                "unit": "Gop/s", "frac": executed / peakMufu, "mufu_executed_per_eval": 1.0625,
+                "unit": "Gop/s", "frac": executed / peakMufu, "mufu_executed_per_eval": perEval,
                 "frac_at_survey_2_mufu_per_eval": 2.0 * evals / (sweepMs * 1e-3) / peakMufu,
                 "traffic": TRAFFIC["c5"][0] * chains / 4096.0, "traffic_source": TRAFFIC["c5"][1],
                 "fp32_pipe_peak_tflops": peakFp32 / 1e12,

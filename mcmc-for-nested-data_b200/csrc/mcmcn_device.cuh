@@ -467,6 +467,9 @@ __device__ __forceinline__ float softplus_t(float eta) {
 __device__ __forceinline__ double softplus_t(double eta) {
     return fmax(eta, 0.0) + log1p(exp(-fabs(eta)));
 }
+#ifndef MCMCN_LOGIT_FOLD_QUADS
+#define MCMCN_LOGIT_FOLD_QUADS 16
+#endif
 struct Logit {
     static constexpr int P = 2;
     static constexpr int UNIT = 8;
@@ -537,15 +540,22 @@ struct Logit {
         // the 1-3 observations of the last, partial quad join the first fold (at most 19 factors)
         const float* xr = blk + (size_t)nq * UNIT;
         for (int j = 0; j < rem; ++j) MCMCN_LOGIT_OBS(xr[j], xr[4 + j])
-        for (int q0 = 0; q0 < nq; q0 += 4) {
+        // MCMCN_LOGIT_FOLD_QUADS quads (x 4 observations) per fold: one lg2 and one FP32 -> FP64 conversion (both on
+        // the XU pipe that bounds this loop) per fold and chain.  16 quads: the product of up to 67 factors in
+        // (1, 2] stays below 2^67, and its 67 roundings (4e-6 relative) move the logarithm by 6e-6 absolute --
+        // against group log-likelihoods of tens, inside the 1e-5 relative bar with a wide margin.
+        for (int q0 = 0; q0 < nq; q0 += MCMCN_LOGIT_FOLD_QUADS) {
+            const int qend = min(nq, q0 + MCMCN_LOGIT_FOLD_QUADS);
+            for (int q1 = q0; q1 < qend; q1 += 4) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (q0 + u < nq) {
-                    float x4[4], y4[4];
-                    Vec4<float>::load(blk + (size_t)(q0 + u) * UNIT, x4);
-                    Vec4<float>::load(blk + (size_t)(q0 + u) * UNIT + 4, y4);
+                for (int u = 0; u < 4; ++u) {
+                    if (q1 + u < qend) {
+                        float x4[4], y4[4];
+                        Vec4<float>::load(blk + (size_t)(q1 + u) * UNIT, x4);
+                        Vec4<float>::load(blk + (size_t)(q1 + u) * UNIT + 4, y4);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) MCMCN_LOGIT_OBS(x4[j], y4[j])
+                        for (int j = 0; j < 4; ++j) MCMCN_LOGIT_OBS(x4[j], y4[j])
+                    }
                 }
             }
             MCMCN_LOGIT_FOLD()
