@@ -1,57 +1,40 @@
 #!/usr/bin/env python
-"""The reference's Gaussian-distribution example (example/distribution.py) on the B200 engine.
+"""BASELINE config 1 on the B200 engine: the reference's Gaussian-distribution example
+(example/distribution.py: 10 groups x 10 responses, parameters a, b, c, 2 chains x 1,000 iterations).
 
     python examples/distribution.py [partial|none|complete]
 
-Same model, data (numpy.random.seed(12345)), chain counts and priors as the reference; the only
-change is that the objective is a device-function handle instead of a Python closure."""
-
-import argparse
-import os
-import sys
+Every parameter j has a group mean mu_j[g] ~ N(0, 1) and one sd_j ~ Gamma(1); an observation of group g
+contributes sum_j log N(theta_j | mu_j[g], sd_j).  The numbers come off numpy's global stream seeded
+with 12345 in the reference's order (per name: the 10 means, then the sd), so the data are the
+reference's; the objective is the registry's device function instead of a Python closure."""
 
 import numpy
 import scipy.stats
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "mcmc-for-nested-data_b200"))
-
-from posteriorSampling import samplePosterior  # noqa: E402
-from sampleDiagnosis import diagnoseSamples  # noqa: E402
-from objectives import Objective  # noqa: E402
+from common import Workload, poolingFromCommandLine
+from objectives import Objective
 
 numpy.random.seed(12345)
 
-
-def getFunction(parameterName, nGroups, nResponsesPerGroup):
-    """example/distribution.py:16-47: mu_j ~ N(0,1) per group, sd_j ~ Gamma(1) per name."""
-    trueValueString = "\nTrue value:\n"
-    mu, sd = [], []
-    for i, name in enumerate(parameterName):
-        m = numpy.random.normal(loc=0, scale=1, size=nGroups)
-        s = numpy.random.gamma(1)
-        mu.append(m)
-        sd.append(s)
-        trueValueString += "\t%s: {mean: %.2f, var: %.2f}\n" % (name, numpy.mean(m), numpy.var(m))
-    objective = Objective.gaussian_distribution(numpy.array(mu), numpy.array(sd), nResponsesPerGroup)
-    prior = [scipy.stats.norm(loc=0, scale=1) for name in parameterName]
-    return objective, prior, trueValueString
+CONFIG = Workload("Example MCMC to sample from Gaussian distribution.", "./example/sample/distribution/",
+                  names=("a", "b", "c"), groups=10, responses=10, chains=2, iterations=1000, retained=100,
+                  nProcesses=1)
 
 
-def main(pooling):
-    nChains, nIter, nSamples = 2, 1000, 100
-    outputDirectory = "./example/sample/distribution/"
-    parameterName = ("a", "b", "c")
-    nGroups, nResponsesPerGroup = 10, 10
-    objective, prior, trueValueString = getFunction(parameterName, nGroups, nResponsesPerGroup)
-    samplePosterior(nChains, nIter, nSamples, parameterName, nGroups, nResponsesPerGroup,
-                    pooling, objective, outputDirectory, priorDistribution=prior, nProcesses=1)
-    print(trueValueString)
-    diagnoseSamples(outputDirectory)
+def mockData(config):
+    means = numpy.empty((len(config.names), config.groups))
+    sds = numpy.empty(len(config.names))
+    for j in range(len(config.names)):
+        means[j] = numpy.random.normal(0.0, 1.0, config.groups)
+        sds[j] = numpy.random.gamma(1)
+    truth = "\nTrue value:\n" + "".join("\t%s: {mean: %.2f, var: %.2f}\n" % (name, means[j].mean(), means[j].var())
+                                          for j, name in enumerate(config.names))
+    return means, sds, truth
 
 
 if __name__ == "__main__":
-    parser = argparse.ArgumentParser(description="Example MCMC to sample from Gaussian distribution.")
-    parser.add_argument("pooling", nargs="?", default="partial",
-                        help="Pooling method (optional) : partial, complete or none. Default is partial.")
-    main(parser.parse_args().pooling)
+    pooling = poolingFromCommandLine(CONFIG.title)
+    means, sds, truth = mockData(CONFIG)
+    CONFIG.samplerOptions["priorDistribution"] = [scipy.stats.norm(loc=0, scale=1) for _ in CONFIG.names]
+    CONFIG.run(pooling, Objective.gaussian_distribution(means, sds, CONFIG.responses), truth)
