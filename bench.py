@@ -50,9 +50,9 @@ REF_RUNNER = os.path.join(ROOT, "baseline", "run_reference.py")
 REF_STAGED = os.path.join(ROOT, "baseline", "_ref", "posteriorSampling.py")
 # DRAM bytes per step-kernel launch from the committed `ncu --set full` captures (dram__bytes_read.sum +
 # dram__bytes_write.sum); they cannot be measured outside a profiler, so the capture is named beside the number
-TRAFFIC = {"tc": (199.9e6, "profiles/r1_final_tc_kernel_ncu_summary.txt (1,024 chains)"),
+TRAFFIC = {"tc": (199.8e6, "profiles/r2_tc_kernel_ncu_summary.txt (1,024 chains: 180.2 MB read + 19.6 MB written)"),
            "pipe": (204.2e6, "profiles/r1_sweep_kernel_ncu_summary.txt (1,024 chains)"),
-           "c5": (2.499e9, "profiles/r1_c5_kernel_ncu_summary.txt (4,096 chains)")}
+           "c5": (2.499e9, "profiles/r2_c5_kernel_ncu_summary.txt (4,096 chains: 1.673 GB read + 0.826 GB written)")}
 
 
 def fixedPriors(pooling, coef):
