@@ -566,8 +566,10 @@ class Engine(object):
         sd = numpy.sqrt(sigma2)
         for c in range(nC):      # name-major, group-minor: one call draws what P calls of G would (the stream is sequential)
             theta[:, :, c] = rss[c].standard_normal((P, G)) * sd[:, c, None] + mu[:, c, None]
-        lprior = hostNormLogpdf(theta, mu[:, None, :], sd[:, None, :])
-        self.setState(theta, numpy.full((G, nC), numpy.nan), lprior, mu, sigma2)
+        # The stored log-priors only matter if a group has to be redrawn below (they are then STALE values of the
+        # first draw, :284-288; the kernels otherwise recompute the group-level log-prior from mu, sigma2): they
+        # are formed when that first happens, from the first draw, not for every run (0.25 s per 1,000 chains at C3).
+        self.setState(theta, numpy.full((G, nC), numpy.nan), None, mu, sigma2)
         ll = numpy.full((G, nC), numpy.nan)
         for attempt in range(100000):
             cur = self.groupLogLikelihood()[:, :nC].cpu().numpy()
@@ -575,6 +577,8 @@ class Engine(object):
             ll[fin] = cur[fin]
             if fin.all():
                 break
+            if not self.lpriorStale:
+                self._up(self.lprior, hostNormLogpdf(theta, mu[:, None, :], sd[:, None, :]))
             for c in numpy.nonzero(~fin.all(axis=0))[0]:
                 bad = numpy.nonzero(~fin[:, c])[0]
                 for p in range(P):                               # log-prior left stale, :284-288
