@@ -106,6 +106,32 @@ def test_start_state_equals_reference_chain(pooling):
             numpy.testing.assert_allclose(st["lprior"][:, :, c], oc.logPrior, rtol=1e-14)
 
 
+def test_start_state_with_redrawn_groups_keeps_the_stale_log_priors():
+    """Partial pooling, a start range that makes many group-level noise sds negative: the groups whose
+    log-likelihood is not finite are redrawn (:746-758) from the chain's stream, and their stored log-priors
+    stay those of the FIRST draw (:284-288) -- theta, log-likelihoods and the stale log-priors must
+    equal the reference chain's."""
+    from engine import Engine
+    meta, obj, prior = _regCase()
+    names = tuple(meta["parameterName"])
+    ranges = dict(meta["startingPointValueRange"], sigma=[0.01, 0.2])
+    nC = 6
+    eng = Engine(parity.deviceObjective(obj, 10, "fp64"), 10, 10, "partial", nC, chainId0=0)
+    eng.initialise(names, ranges, False)
+    assert eng.lpriorStale
+    st = eng.getState()
+    redrawn = 0
+    for c in range(nC):
+        oc = po.OracleChain(c, c, 100, 50, names, 10, 10, "partial", obj, prior, False, ranges)
+        numpy.testing.assert_array_equal(st["theta"][:, :, c], oc.value)
+        numpy.testing.assert_allclose(st["ll"][:, c], oc.LL, rtol=1e-12)
+        numpy.testing.assert_allclose(st["lprior"][:, :, c], oc.logPrior, rtol=1e-13, atol=1e-13)
+        with numpy.errstate(all="ignore"):
+            fresh = scipy.stats.norm(oc.mu[:, None], numpy.sqrt(oc.sigma2)[:, None]).logpdf(oc.value)
+        redrawn += int((numpy.abs(fresh - oc.logPrior) > 1e-9).sum())
+    assert redrawn > 0            # some stored log-priors really are stale
+
+
 def test_mle_start_close_to_scipy_nelder_mead():
     from engine import Engine
     meta, obj, prior = _regCase()
