@@ -1,16 +1,39 @@
-import sys, os, time, cProfile, pstats
-sys.path[:0]=['/root/repo','/root/repo/mcmc-for-nested-data_b200']
-import torch
+#!/usr/bin/env python
+"""Where samplePosterior's start-up goes at config-3 size (GPU box): cProfile of a short call
+(1,024 chains x 200 iterations, binary store in /dev/shm) after two warm calls.
+usage: python tools/profile_startup.py"""
+import cProfile
+import os
+import pstats
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "mcmc-for-nested-data_b200")]
+import torch  # noqa: E402
+
 torch.zeros(1).cuda()
-import posteriorSampling as ps
-from objectives import Objective
-from workloads import makeWorkload
-X,y,names,ranges=makeWorkload(1024,200,8)
-ps.CSV_VALUE_LIMIT=0; ps.STORE_DTYPE="float32"
+import posteriorSampling as ps  # noqa: E402
+from objectives import Objective  # noqa: E402
+from workloads import makeWorkload  # noqa: E402
+
+X, y, names, ranges = makeWorkload(1024, 200, 8)
+ps.CSV_VALUE_LIMIT = 0
+ps.STORE_DTYPE = "float32"
+
+
 def run():
-    h=Objective.linear_regression(X,y)
-    ps.samplePosterior(1024,200,20,names,1024,200,"partial",h,"/dev/shm/prof_start",saveLogLikelihood=False,startingPointValueRange=ranges,displayProgress=False)
+    handle = Objective.linear_regression(X, y)
+    ps.samplePosterior(1024, 200, 20, names, 1024, 200, "partial", handle, "/dev/shm/mcmcn_profile_startup",
+                       saveLogLikelihood=False, startingPointValueRange=ranges, displayProgress=False)
+
+
 run()
-t=time.time(); run(); print("second call wall", time.time()-t)
-pr=cProfile.Profile(); pr.enable(); run(); pr.disable()
+t = time.time()
+run()
+print("second call wall", time.time() - t)
+pr = cProfile.Profile()
+pr.enable()
+run()
+pr.disable()
 pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
