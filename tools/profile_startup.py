@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Where samplePosterior's start-up goes at config-3 size (GPU box): cProfile of a short call
 (1,024 chains x 200 iterations, binary store in /dev/shm) after two warm calls.
-usage: python tools/profile_startup.py"""
+usage: python tools/profile_startup.py [chains]"""
 import cProfile
 import os
 import pstats
@@ -17,6 +17,7 @@ import posteriorSampling as ps  # noqa: E402
 from objectives import Objective  # noqa: E402
 from workloads import makeWorkload  # noqa: E402
 
+CHAINS = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 X, y, names, ranges = makeWorkload(1024, 200, 8)
 ps.CSV_VALUE_LIMIT = 0
 ps.STORE_DTYPE = "float32"
@@ -24,7 +25,7 @@ ps.STORE_DTYPE = "float32"
 
 def run():
     handle = Objective.linear_regression(X, y)
-    ps.samplePosterior(1024, 200, 20, names, 1024, 200, "partial", handle, "/dev/shm/mcmcn_profile_startup",
+    ps.samplePosterior(CHAINS, 200, 20, names, 1024, 200, "partial", handle, "/dev/shm/mcmcn_profile_startup",
                        saveLogLikelihood=False, startingPointValueRange=ranges, displayProgress=False)
 
 
