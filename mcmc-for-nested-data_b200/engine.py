@@ -592,10 +592,11 @@ class Engine(object):
                 break
             if not self.lpriorStale:
                 self._upChainMajor(self.lprior, hostNormLogpdf(thetaC, muC, sdC))
-            for c in numpy.nonzero(~fin.all(axis=0))[0]:
-                bad = numpy.nonzero(~fin[:, c])[0]
-                for p in range(P):                               # log-prior left stale, :284-288
-                    thetaC[c, p, bad] = rss[c].standard_normal(len(bad)) * sd[p, c] + mu[p, c]
+            badT = ~fin.T                                        # [nC][G]
+            for c in numpy.nonzero(badT.any(axis=1))[0]:
+                bad = numpy.nonzero(badT[c])[0]
+                # name by name, the bad groups in order (:755-758): one call draws what P calls would; log-prior left stale
+                thetaC[c][:, bad] = rss[c].standard_normal((P, len(bad))) * sdC[c] + muC[c]
             self.lpriorStale = True
             self._upChainMajor(self.theta, thetaC)
         else:
