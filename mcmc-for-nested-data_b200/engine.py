@@ -590,8 +590,12 @@ class Engine(object):
             ll[fin] = cur[fin]
             if fin.all():
                 break
-            if not self.lpriorStale:
-                self._upChainMajor(self.lprior, hostNormLogpdf(thetaC, muC, sdC))
+            if not self.lpriorStale:                             # scipy.stats.norm(mu, sd).logpdf(theta) of the first draw, on the device
+                hmu, hsd = self.hyper[0][:, None, :], self.hyper[2][:, None, :]
+                y = (self.theta - hmu) / hsd
+                lp = -(y * y) / 2.0 - _NORM_PDF_LOGC - torch.log(hsd)
+                self.lprior.copy_(torch.where(~(hsd > 0) | torch.isnan(y), torch.full_like(lp, float("nan")), lp))
+                del y, lp
             badT = ~fin.T                                        # [nC][G]
             for c in numpy.nonzero(badT.any(axis=1))[0]:
                 bad = numpy.nonzero(badT[c])[0]
