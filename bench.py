@@ -221,14 +221,14 @@ def runReference(args):
         kind, sample = "reference", referenceSampleText(args, rec) + "; per step"
         # calibration at the FULL shape, once: one process, and one process per core
         if not args.no_calibration:
-            one = referenceRun(args, args.groups, 1, 1, args.ref_iters)
-            allc = referenceRun(args, args.groups, cores, cores, args.ref_iters)
+            one = referenceRun(args, args.groups, 1, 1, args.ref_calibration_iters)
+            allc = referenceRun(args, args.groups, cores, cores, args.ref_calibration_iters)
             extra = {"full_shape_1_process": {"value": one["chains"] * one["iters"] / max(one["loop_s"]), "unit": UNIT,
                                               "loop_s": max(one["loop_s"]), "wall_s": one["wall_s"]},
                      "full_shape_1_process_per_core": {"value": allc["chains"] * allc["iters"] / max(allc["loop_s"]),
                                                        "unit": UNIT, "cores": cores, "loop_s": max(allc["loop_s"]),
                                                        "wall_s": allc["wall_s"]},
-                     "iterations": args.ref_iters, "numpy": one["numpy"], "scipy": one["scipy"],
+                     "iterations": args.ref_calibration_iters, "numpy": one["numpy"], "scipy": one["scipy"],
                      "note": "the unmodified reference on ALL %d groups: the figure the scaled per-step rate must "
                              "reproduce" % args.groups}
     else:
@@ -686,6 +686,8 @@ def main():
     ap.add_argument("--ref-iters", type=int, default=6, help="unmodified reference: iterations per step (>= 6)")
     ap.add_argument("--ref-groups", type=int, default=64, help="unmodified reference: groups of the per-step sample")
     ap.add_argument("--port", action="store_true", help="--impl reference: time the oracle port even if baseline/_ref is staged")
+    ap.add_argument("--ref-calibration-iters", type=int, default=30,
+                    help="--impl reference: iterations of the two runs on ALL groups (one process; one process per core)")
     ap.add_argument("--no-calibration", action="store_true", help="--impl reference: skip the two full-shape runs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
