@@ -121,6 +121,35 @@ def test_production_kernels_with_many_groups_equal_general_bit_for_bit(monkeypat
     _assertIdentical(prod, gen)
 
 
+@pytest.mark.parametrize("noTc", [False, True])
+def test_same_seed_twice_is_bit_identical(noTc, monkeypatch):
+    """No atomics, no order-dependent reductions: two runs from the same seed and start give the same bits
+    (compute-sanitizer's racecheck is not available on the GPU pool; a shared-memory, tensor-memory or
+    TMA-stage hazard in the step kernels would show up here as a difference between runs).  C3's group
+    shape, four chain blocks, group ranges of several groups, across a tune iteration."""
+    import torch
+    from engine import Engine, SampleStore
+    if noTc:
+        monkeypatch.setenv("MCMCN_NO_TC", "1")
+    else:
+        monkeypatch.delenv("MCMCN_NO_TC", raising=False)
+    G, R, K, nC = 96, 200, 8, 500
+    obj, names, nResp, ranges = parity.syntheticRegression(G=G, R=R, K=K)
+    out = []
+    for rep in range(3):
+        eng = Engine(parity.deviceObjective(obj, nResp, "fp32"), G, nResp, "partial", nC, chainId0=5, seed=77)
+        eng.initialise(names, ranges)
+        store = SampleStore(eng, 10, torch.float64)
+        eng.run(0, 140, 120, 2, store=store)
+        torch.cuda.synchronize()
+        st = eng.getState()
+        out.append((st["theta"], st["ll"], st["scale"], st["mu"], st["sigma2"], store.hostArray()))
+        del eng, store
+    for other in out[1:]:
+        for a, b in zip(out[0], other):
+            numpy.testing.assert_array_equal(a, b)
+
+
 def test_results_do_not_depend_on_how_many_chains_share_the_gpu():
     """Philox and the start-state streams are keyed by the global chain id, and every sum over groups is taken
     in a fixed order whatever the launch shape (the one-pass Gibbs kernel picks its block shape from the chain
