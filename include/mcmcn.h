@@ -289,6 +289,25 @@ int mcmcn_user_objective_compile(const char* source, int32_t n_params, int32_t o
                                  int32_t hdr_floats, int32_t precision, void** out_handle);
 int mcmcn_user_objective_free(void* handle);
 
+/* ---- the chains' host random streams of the start state (host memory, no device work) ----
+ * The reference runs each chain in its own process and seeds numpy's global legacy generator with the chain
+ * index (posteriorSampling.py:225, :1015); the start state is drawn from that stream: numpy.random.uniform per
+ * parameter (:1069-1077) and, under partial pooling, numpy.random.normal per parameter and group (:738-758).
+ * Stream i of a handle is numpy.random.RandomState(seed0 + i): MT19937 seeded by init_genrand, 53-bit doubles,
+ * the polar normal with its cached second value -- bit for bit.  `threads` host threads share the listed streams.
+ *   uniform: for every listed stream j, `count` draws low[i] + (high[i] - low[i]) * u_i  -> out[j][i]
+ *   normal:  for every listed stream j, out[out_off[j] .. out_off[j+1]) standard normals, in order
+ *   get/set_state: numpy's ('MT19937', key[624], pos, has_gauss, cached_gaussian) tuple of one stream, to hand
+ *            a stream to scipy (`prior.rvs(random_state=...)`, :1079-1081) and take it back. */
+int mcmcn_streams_create(int64_t n, int64_t seed0, int32_t threads, void** out_handle);
+int mcmcn_streams_free(void* handle);
+int mcmcn_streams_uniform(void* handle, const int64_t* which, int64_t n_which, int32_t count, const double* low,
+                          const double* high, double* out, int32_t threads);
+int mcmcn_streams_normal(void* handle, const int64_t* which, int64_t n_which, const int64_t* out_off, double* out,
+                         int32_t threads);
+int mcmcn_streams_get_state(void* handle, int64_t i, uint32_t* key624, int32_t* pos, int32_t* has_gauss, double* gauss);
+int mcmcn_streams_set_state(void* handle, int64_t i, const uint32_t* key624, int32_t pos, int32_t has_gauss, double gauss);
+
 /* Known-answer hook for tests: out[0..3] = Philox4x32-10(counter[0..3], key[0..1]) computed on
  * the device (all three are device pointers to uint32). */
 int mcmcn_debug_philox(const void* counter, const void* key, void* out);

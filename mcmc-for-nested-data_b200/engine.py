@@ -550,10 +550,10 @@ class Engine(object):
         """Reference start-up, all chains at once.  Each chain draws from its own legacy
         MT19937 stream seeded with its global chain id (seed = chain, :225, :1015), in the
         reference's order, so start states equal the reference's."""
-        from startpoint import findStartingPoints
+        from startpoint import findStartingPoints, ChainStreams
         P, G, nC = self.P, self.G, self.nChains
-        rss = [numpy.random.RandomState(self.chainId0 + c) for c in range(nC)]
-        x = findStartingPoints(self, rss, parameterName, startingPointValueRange, startWithMLE, logger)
+        streams = ChainStreams(nC, self.chainId0)
+        x = findStartingPoints(self, streams, parameterName, startingPointValueRange, startWithMLE, logger)
         self.startingPoint = x                                   # [P][nC]
 
         theta = numpy.zeros((P, G, nC))
@@ -572,9 +572,8 @@ class Engine(object):
         sigma2 = numpy.sqrt(numpy.abs(x) / 10.)                  # sic (:730)
         sd = numpy.sqrt(sigma2)
         muC, sdC = numpy.ascontiguousarray(mu.T)[:, :, None], numpy.ascontiguousarray(sd.T)[:, :, None]   # [nC][P][1]
-        thetaC = numpy.empty((nC, P, G))
-        for c in range(nC):      # name-major, group-minor: one call draws what P calls of G would (the stream is sequential)
-            thetaC[c] = rss[c].standard_normal((P, G))
+        # name-major, group-minor: one run of P * G draws per chain is what P calls of G would draw (the stream is sequential)
+        thetaC = streams.standardNormal(numpy.arange(nC), P * G).reshape(nC, P, G)
         thetaC *= sdC
         thetaC += muC
         # The stored log-priors only matter if a group has to be redrawn below (they are then STALE values of the
@@ -597,10 +596,15 @@ class Engine(object):
                 self.lprior.copy_(torch.where(~(hsd > 0) | torch.isnan(y), torch.full_like(lp, float("nan")), lp))
                 del y, lp
             badT = ~fin.T                                        # [nC][G]
-            for c in numpy.nonzero(badT.any(axis=1))[0]:
+            redo = numpy.nonzero(badT.any(axis=1))[0]
+            nBad = badT[redo].sum(axis=1)
+            z = streams.standardNormal(redo, P * nBad)
+            at = 0
+            for c, nb in zip(redo, nBad):
                 bad = numpy.nonzero(badT[c])[0]
-                # name by name, the bad groups in order (:755-758): one call draws what P calls would; log-prior left stale
-                thetaC[c][:, bad] = rss[c].standard_normal((P, len(bad))) * sdC[c] + muC[c]
+                # name by name, the bad groups in order (:755-758): one run draws what P calls would; log-prior left stale
+                thetaC[c][:, bad] = z[at:at + P * nb].reshape(P, nb) * sdC[c] + muC[c]
+                at += P * nb
             self.lpriorStale = True
             self._upChainMajor(self.theta, thetaC)
         else:

@@ -122,6 +122,15 @@ PROTOTYPES = {
                                                     ctypes.c_int32, ctypes.c_int32,
                                                     ctypes.POINTER(c_void_p)]),
     "mcmcn_user_objective_free": (ctypes.c_int, [c_void_p]),
+    "mcmcn_streams_create": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(c_void_p)]),
+    "mcmcn_streams_free": (ctypes.c_int, [c_void_p]),
+    "mcmcn_streams_uniform": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int32, c_void_p, c_void_p,
+                                             c_void_p, ctypes.c_int32]),
+    "mcmcn_streams_normal": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, c_void_p, c_void_p, ctypes.c_int32]),
+    "mcmcn_streams_get_state": (ctypes.c_int, [c_void_p, ctypes.c_int64, c_void_p, ctypes.POINTER(ctypes.c_int32),
+                                               ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double)]),
+    "mcmcn_streams_set_state": (ctypes.c_int, [c_void_p, ctypes.c_int64, c_void_p, ctypes.c_int32, ctypes.c_int32,
+                                               ctypes.c_double]),
     "mcmcn_debug_philox": (ctypes.c_int, [c_void_p, c_void_p, c_void_p]),
     "mcmcn_debug_draws": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_double,
                                          c_void_p, c_void_p]),

@@ -9,11 +9,82 @@ options are unknown to current scipy and ignored, so the defaults xatol = fatol 
 apply) but advances all chains in lock-step, masking the branch each chain takes.
 """
 
+import ctypes
+import os
+
 import numpy
 
+import mcmcn_native as nat
 
-def findStartingPoints(engine, rss, parameterName, valueRange, startWithMLE, logger=None):
-    """Returns x[P][nChains].  ``rss[c]`` is chain c's legacy RandomState."""
+
+def _hostThreads():
+    """Host threads for the chains' start-state streams: the cores of the box shared among its ranks."""
+    if os.environ.get("MCMCN_START_THREADS"):
+        return max(1, int(os.environ["MCMCN_START_THREADS"]))
+    return max(1, min(32, (os.cpu_count() or 4) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+
+
+class ChainStreams(object):
+    """The chains' own legacy numpy streams (the reference seeds each chain's process with the chain index,
+    posteriorSampling.py:225, :1015): stream c equals ``numpy.random.RandomState(seed0 + c)`` bit for bit,
+    held and advanced natively (``mcmcn_streams_*``, csrc/mcmcn_streams.cu) by host threads instead of one
+    Python object per chain."""
+
+    def __init__(self, nChains, seed0=0):
+        self.n = int(nChains)
+        self.threads = _hostThreads()
+        h = ctypes.c_void_p()
+        nat.call("mcmcn_streams_create", self.n, int(seed0), self.threads, ctypes.byref(h))
+        self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            nat.load().mcmcn_streams_free(h)
+
+    @staticmethod
+    def _which(chains):
+        return numpy.ascontiguousarray(chains, dtype=numpy.int64)
+
+    def uniform(self, chains, low, high):
+        """[len(chains)][len(low)]: for each listed chain, in order i, ``uniform(low[i], high[i])``."""
+        which = self._which(chains)
+        low, high = numpy.ascontiguousarray(low, dtype=numpy.float64), numpy.ascontiguousarray(high, dtype=numpy.float64)
+        out = numpy.empty((len(which), len(low)))
+        nat.call("mcmcn_streams_uniform", self._h, which.ctypes.data, len(which), len(low), low.ctypes.data,
+                 high.ctypes.data, out.ctypes.data, self.threads)
+        return out
+
+    def standardNormal(self, chains, counts):
+        """Flat array: counts[j] (or the one count) ``standard_normal`` draws of each listed chain, chain after chain."""
+        which = self._which(chains)
+        counts = numpy.broadcast_to(numpy.asarray(counts, dtype=numpy.int64), (len(which),))
+        off = numpy.zeros(len(which) + 1, dtype=numpy.int64)
+        off[1:] = numpy.cumsum(counts)
+        out = numpy.empty(int(off[-1]))
+        nat.call("mcmcn_streams_normal", self._h, which.ctypes.data, len(which), off.ctypes.data, out.ctypes.data,
+                 self.threads)
+        return out
+
+    def randomState(self, c):
+        """Chain c's stream as a numpy RandomState (for ``scipy_prior.rvs(random_state=...)``); give it back
+        with ``adopt`` after drawing."""
+        key = numpy.empty(624, dtype=numpy.uint32)
+        pos, has, g = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_double()
+        nat.call("mcmcn_streams_get_state", self._h, int(c), key.ctypes.data, ctypes.byref(pos), ctypes.byref(has),
+                 ctypes.byref(g))
+        rs = numpy.random.RandomState(0)
+        rs.set_state(("MT19937", key, pos.value, has.value, g.value))
+        return rs
+
+    def adopt(self, c, rs):
+        _, key, pos, has, g = rs.get_state()
+        key = numpy.ascontiguousarray(key, dtype=numpy.uint32)
+        nat.call("mcmcn_streams_set_state", self._h, int(c), key.ctypes.data, int(pos), int(has), float(g))
+
+
+def findStartingPoints(engine, streams, parameterName, valueRange, startWithMLE, logger=None):
+    """Returns x[P][nChains].  ``streams`` holds every chain's legacy numpy stream (ChainStreams)."""
     P, nC = engine.P, engine.nChains
     if valueRange is None:
         valueRange = {}
@@ -21,16 +92,25 @@ def findStartingPoints(engine, rss, parameterName, valueRange, startWithMLE, log
         if name not in valueRange and engine.priorScipy is None:
             # the reference calls the non-existent numpy.random.norm here (:1079)
             raise ValueError("parameter %r needs a startingPointValueRange entry or a prior" % (name,))
+    allRanged = all(name in valueRange for name in parameterName)
+    if allRanged:
+        low = [valueRange[name][0] for name in parameterName]
+        high = [valueRange[name][1] for name in parameterName]
     x = numpy.zeros((P, nC))
     pending = list(range(nC))
     counter = 0
     while pending:
-        for c in pending:
-            for i, name in enumerate(parameterName):
-                if name in valueRange:
-                    x[i, c] = rss[c].uniform(low=valueRange[name][0], high=valueRange[name][1])
-                else:
-                    x[i, c] = engine.priorScipy[i].rvs(random_state=rss[c])
+        if allRanged:                                   # one native call: P uniforms of every pending chain (:1069-1077)
+            x[:, pending] = streams.uniform(pending, low, high).T
+        else:                                           # a prior's own sampler in between (:1079-1081): chain by chain
+            for c in pending:
+                rs = streams.randomState(c)
+                for i, name in enumerate(parameterName):
+                    if name in valueRange:
+                        x[i, c] = rs.uniform(low=valueRange[name][0], high=valueRange[name][1])
+                    else:
+                        x[i, c] = engine.priorScipy[i].rvs(random_state=rs)
+                streams.adopt(c, rs)
         nll = engine.pooledNll(x)
         pending = [c for c in pending if not numpy.isfinite(nll[c])]
         counter += 1

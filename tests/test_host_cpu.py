@@ -294,7 +294,7 @@ def test_batched_nelder_mead_equals_scipy():
 
 
 def test_start_point_search_consumes_the_reference_stream():
-    from startpoint import findStartingPoints
+    from startpoint import findStartingPoints, ChainStreams
     meta = loadGolden("reg_none")
     obj, prior = oracleObjectiveFromMeta(meta)
     names = tuple(meta["parameterName"])
@@ -305,13 +305,47 @@ def test_start_point_search_consumes_the_reference_stream():
 
     for ranges in (meta["startingPointValueRange"], {"b0": [-1, 1]}):       # second: priors for b1, sigma
         eng = _FakeEngine(nll, 3, 4, prior)
-        rss = [numpy.random.RandomState(c) for c in range(4)]
-        x = findStartingPoints(eng, rss, names, ranges, False)
+        x = findStartingPoints(eng, ChainStreams(4), names, ranges, False)
         for c in range(4):
             oc = po.OracleChain(c, c, 20, 10, names, 10, 10, "none", obj, prior, False, ranges)
             numpy.testing.assert_array_equal(x[:, c], oc.startingPoint)
     with pytest.raises(ValueError):
-        findStartingPoints(_FakeEngine(nll, 3, 1, None), [numpy.random.RandomState(0)], names, {"b0": [0, 1]}, False)
+        findStartingPoints(_FakeEngine(nll, 3, 1, None), ChainStreams(1), names, {"b0": [0, 1]}, False)
+
+
+def test_native_chain_streams_equal_numpy_legacy_random_state_bit_for_bit():
+    """csrc/mcmcn_streams.cu: stream c = numpy.random.RandomState(seed0 + c) (the reference seeds each chain's
+    process with the chain index, posteriorSampling.py:225): uniforms, normals with the cached second value,
+    refills of the 624-word block, interleaving, and the hand-over of a stream to numpy and back."""
+    from startpoint import ChainStreams
+    n, seed0 = 37, 1000
+    st = ChainStreams(n, seed0)
+    ref = [numpy.random.RandomState(seed0 + c) for c in range(n)]
+    low, high = [-2.0, 0.5, 1e-3, -1e6], [3.0, 0.75, 7.0, 1e6]
+    u = st.uniform(numpy.arange(n), low, high)
+    want = numpy.array([[r.uniform(low=a, high=b) for a, b in zip(low, high)] for r in ref])
+    numpy.testing.assert_array_equal(u, want)
+    # an odd count leaves a cached normal behind; the next call must return it first
+    z = st.standardNormal(numpy.arange(n), 2001).reshape(n, 2001)
+    numpy.testing.assert_array_equal(z, numpy.array([r.standard_normal(2001) for r in ref]))
+    # a subset with ragged counts, then uniforms again (uniforms do not touch the cached normal)
+    some = numpy.array([5, 0, 36, 17])
+    counts = numpy.array([3, 0, 700, 1])
+    z = st.standardNormal(some, counts)
+    numpy.testing.assert_array_equal(z, numpy.concatenate([ref[c].standard_normal(k) for c, k in zip(some, counts)]))
+    u = st.uniform(some, [0.0], [1.0])[:, 0]
+    numpy.testing.assert_array_equal(u, numpy.array([ref[c].uniform(low=0.0, high=1.0) for c in some]))
+    # hand a stream to numpy / scipy and take it back
+    import scipy.stats
+    rs = st.randomState(17)
+    got = scipy.stats.gamma(2.5, scale=3.0).rvs(size=5, random_state=rs)
+    numpy.testing.assert_array_equal(got, scipy.stats.gamma(2.5, scale=3.0).rvs(size=5, random_state=ref[17]))
+    st.adopt(17, rs)
+    z = st.standardNormal(numpy.arange(n), 11).reshape(n, 11)
+    numpy.testing.assert_array_equal(z, numpy.array([r.standard_normal(11) for r in ref]))
+    # seeds beyond 32 bits are refused, like numpy.random.seed
+    with pytest.raises(RuntimeError):
+        ChainStreams(2, 2 ** 32 - 1)
 
 
 def _gloo_worker(rank, world, port, tmp):
