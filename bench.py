@@ -673,8 +673,9 @@ def main():
     # the whole configuration through samplePosterior (e2e / full_run)
     ap.add_argument("--full-iters", type=int, default=20000, help="config 3: 20k iterations")
     ap.add_argument("--full-samples", type=int, default=1000, help="retained rows per chain (burn 10,000, thin 10)")
-    ap.add_argument("--c4-iters", type=int, default=2000, help="N > 1: iterations of the samplePosterior call on config 4")
-    ap.add_argument("--c4-samples", type=int, default=100)
+    ap.add_argument("--c4-iters", type=int, default=20000, help="N > 1: iterations of the samplePosterior call on config 4 (config 3's 20k)")
+    ap.add_argument("--c4-samples", type=int, default=100, help="retained rows per chain (burn 10,000, thin 100: a 60 GB FP32 store; "
+                                                                "config 3's 1,000 rows x 16,384 chains would be 605 GB)")
     ap.add_argument("--store-dtype", default="float32", choices=["float32", "float64"],
                     help="sample store of the full run (float32 is the store's documented opt-in: 37.8 GB for config 3)")
     ap.add_argument("--output-root", default=None, help="where the full run writes (default /dev/shm, else the temp dir)")

@@ -177,8 +177,8 @@ class SampleStore(object):
         if self.streamed:
             self._chunk, self._fill, self._done = 0, 0, 0          # ring position; rows already handed to the sink
             self._side = torch.cuda.Stream(dev)
-            self._pin = [torch.empty((self.chunkRows, engine.nCol, S), dtype=dtype).pin_memory() for _ in range(2)]
-            self._pinLL = [torch.empty((self.chunkRows, engine.nObservations, S), dtype=torch.float64).pin_memory()
+            self._pin = [torch.empty((self.chunkRows, engine.nCol, S), dtype=dtype, pin_memory=True) for _ in range(2)]
+            self._pinLL = [torch.empty((self.chunkRows, engine.nObservations, S), dtype=torch.float64, pin_memory=True)
                            for _ in range(2)] if logLikelihood else None
             self._copied = [None, None]
             self._pending = []
@@ -573,15 +573,20 @@ class Engine(object):
         sd = numpy.sqrt(sigma2)
         muC, sdC = numpy.ascontiguousarray(mu.T)[:, :, None], numpy.ascontiguousarray(sd.T)[:, :, None]   # [nC][P][1]
         # name-major, group-minor: one run of P * G draws per chain is what P calls of G would draw (the stream is sequential)
-        thetaC = streams.standardNormal(numpy.arange(nC), P * G).reshape(nC, P, G)
-        thetaC *= sdC
-        thetaC += muC
+        z = streams.standardNormal(numpy.arange(nC), P * G).reshape(nC, P, G)
+        thetaC = None                                            # host copy of the state: formed only if a group is redrawn
+        # numpy.random.normal(mu, sd) = mu + sd * z with two roundings (:740): scaled, shifted and transposed on the device
+        # (two separate FP64 kernels, so no fused multiply-add), the normals uploaded as drawn
+        zt = torch.from_numpy(z).to(self.device).permute(1, 2, 0)            # [P][G][nC] view
+        sdD = torch.from_numpy(sd).to(self.device)[:, None, :]
+        muD = torch.from_numpy(mu).to(self.device)[:, None, :]
+        self.theta[..., :nC].copy_(torch.add(torch.mul(zt, sdD), muD))
+        del zt
+        self.ll.fill_(float("nan"))
+        self.setHyper(mu, sigma2)
         # The stored log-priors only matter if a group has to be redrawn below (they are then STALE values of the
         # first draw, :284-288; the kernels otherwise recompute the group-level log-prior from mu, sigma2): they
         # are formed when that first happens, from the first draw, not for every run.
-        self._upChainMajor(self.theta, thetaC)
-        self.ll.fill_(float("nan"))
-        self.setHyper(mu, sigma2)
         ll = numpy.full((G, nC), numpy.nan)
         for attempt in range(100000):
             cur = self.groupLogLikelihood()[:, :nC].cpu().numpy()
@@ -595,15 +600,19 @@ class Engine(object):
                 lp = -(y * y) / 2.0 - _NORM_PDF_LOGC - torch.log(hsd)
                 self.lprior.copy_(torch.where(~(hsd > 0) | torch.isnan(y), torch.full_like(lp, float("nan")), lp))
                 del y, lp
+            if thetaC is None:                                   # the same values as on the device
+                thetaC = z
+                thetaC *= sdC
+                thetaC += muC
             badT = ~fin.T                                        # [nC][G]
             redo = numpy.nonzero(badT.any(axis=1))[0]
             nBad = badT[redo].sum(axis=1)
-            z = streams.standardNormal(redo, P * nBad)
+            zNew = streams.standardNormal(redo, P * nBad)
             at = 0
             for c, nb in zip(redo, nBad):
                 bad = numpy.nonzero(badT[c])[0]
                 # name by name, the bad groups in order (:755-758): one run draws what P calls would; log-prior left stale
-                thetaC[c][:, bad] = z[at:at + P * nb].reshape(P, nb) * sdC[c] + muC[c]
+                thetaC[c][:, bad] = zNew[at:at + P * nb].reshape(P, nb) * sdC[c] + muC[c]
                 at += P * nb
             self.lpriorStale = True
             self._upChainMajor(self.theta, thetaC)
