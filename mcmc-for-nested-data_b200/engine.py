@@ -123,7 +123,9 @@ def _hostThreads(env):
 
 
 WRITER_THREADS = _hostThreads("MCMCN_STORE_THREADS")
-PREFAULT_THREADS = max(1, WRITER_THREADS // 2)
+# as many as writers: the file's pages are populated while the chains burn in and the writers have nothing to do (C3:
+# 37.8 GB in 2.9 s takes eight threads; with four the writers met unpopulated pages and the sampling phase waited)
+PREFAULT_THREADS = int(os.environ.get("MCMCN_PREFAULT_THREADS", WRITER_THREADS))
 
 
 def retainedCount(lo, hi, burn, thin):
@@ -141,16 +143,18 @@ class SampleStore(object):
     streamed (``path`` given): the device holds a ring of two chunks of ``chunkRows`` rows.  When the
         chains have filled one chunk it is copied to pinned host memory on a side stream while they
         fill the other, and then written into ``path``, a .npy file [nRows][ncol][nChains] opened with
-        numpy.lib.format.open_memmap.  Device and pinned memory are 2 x chunkBytes each whatever the
-        run length (posteriorSampling.py:898-909, :933-936 appends a CSV row per retained iteration;
-        this is the same stream of rows in binary).  ``Engine.run`` splits its iterations at chunk
-        boundaries; ``finish()`` drains the ring.
+        numpy.lib.format.open_memmap, by a retire thread (which waits for the copy and deals the rows to
+        the writer threads) -- the thread that launches the kernels only waits if the writers are a whole
+        ring behind.  Device and pinned memory are 2 x chunkBytes each whatever the run length
+        (posteriorSampling.py:898-909, :933-936 appends a CSV row per retained iteration; this is the
+        same stream of rows in binary).  ``Engine.run`` splits its iterations at chunk boundaries;
+        ``finish()`` drains the ring.
     ``logLikSink(row0, block)`` receives the pointwise log-likelihood rows as host arrays
     [rows][N][nChains] in row order (streamed or not, at ``finish()`` when resident).
     """
 
     def __init__(self, engine, nRows, dtype=torch.float64, path=None, logLikelihood=False, logLikSink=None,
-                 chunkBytes=512 << 20):
+                 chunkBytes=128 << 20):
         self.engine = engine
         self.nRows = int(nRows)
         self.dtype = dtype
@@ -177,13 +181,23 @@ class SampleStore(object):
         if self.streamed:
             self._chunk, self._fill, self._done = 0, 0, 0          # ring position; rows already handed to the sink
             self._side = torch.cuda.Stream(dev)
-            self._pin = [torch.empty((self.chunkRows, engine.nCol, S), dtype=dtype, pin_memory=True) for _ in range(2)]
-            self._pinLL = [torch.empty((self.chunkRows, engine.nObservations, S), dtype=torch.float64, pin_memory=True)
-                           for _ in range(2)] if logLikelihood else None
+            # The pinned staging buffers (2 x chunkBytes: 0.6 s of cudaHostAlloc at 1 GB) are allocated by a background
+            # thread: the first chunk is full only after the burn-in, so the chains start without waiting for them.
+            self._pin, self._pinLL = None, None
+
+            def allocatePinned():
+                torch.cuda.set_device(dev)                          # the thread's own current device (default: 0)
+                pin = [torch.empty((self.chunkRows, engine.nCol, S), dtype=dtype, pin_memory=True) for _ in range(2)]
+                pinLL = [torch.empty((self.chunkRows, engine.nObservations, S), dtype=torch.float64, pin_memory=True)
+                         for _ in range(2)] if logLikelihood else None
+                self._pin, self._pinLL = pin, pinLL
+            self._pinThread = threading.Thread(target=allocatePinned, daemon=True)
+            self._pinThread.start()
             self._copied = [None, None]
-            self._pending = []
+            self._written = [None, None]                            # future of the retire job that reads pinned slot c
             import concurrent.futures
             self._writers = concurrent.futures.ThreadPoolExecutor(max_workers=WRITER_THREADS)
+            self._retirer = concurrent.futures.ThreadPoolExecutor(max_workers=1)     # one thread: chunks retire in order
             npdt = numpy.float64 if dtype == torch.float64 else numpy.float32
             self.sink = numpy.lib.format.open_memmap(path, mode="w+", dtype=npdt,
                                                      shape=(self.nRows, engine.nCol, engine.nChains))
@@ -241,6 +255,13 @@ class SampleStore(object):
         c, n = self._chunk, self._fill
         if n == 0:
             return
+        if self._pinThread is not None:
+            self._pinThread.join()
+            self._pinThread = None
+            if self._pin is None:
+                raise RuntimeError("could not allocate the pinned staging buffers of the sample store")
+        if self._written[c] is not None:            # pinned slot c still being written to the file: a whole ring behind
+            self._written[c].result()               # (re-raises what the retire thread raised)
         main = torch.cuda.current_stream(self.engine.device)
         filled = torch.cuda.Event()
         filled.record(main)
@@ -253,17 +274,15 @@ class SampleStore(object):
             done = torch.cuda.Event()
             done.record(self._side)
         self._copied[c] = done
-        self._pending.append((c, n, self._done))
+        self._written[c] = self._retirer.submit(self._retire, (c, n, self._done, done))
         self._done += n
         self._chunk, self._fill = 1 - c, 0
-        while len(self._pending) > 1:            # the chunk before this one: its copy ran while this one filled
-            self._retire(self._pending.pop(0))
         if self._copied[self._chunk] is not None:    # the chains may overwrite the other chunk once it has left the device
             main.wait_event(self._copied[self._chunk])
 
     def _retire(self, item):
-        c, n, row0 = item
-        self._copied[c].synchronize()
+        c, n, row0, copied = item
+        copied.synchronize()
         nC = self.engine.nChains
         src = self._pin[c][:n].numpy()
         # pinned memory -> the file's pages on WRITER_THREADS host threads (numpy copies release the GIL; one
@@ -288,8 +307,13 @@ class SampleStore(object):
         """Drain the ring and close the file (streamed), or hand the log-likelihood rows over (resident)."""
         if self.streamed:
             self._flushChunk()
-            while self._pending:
-                self._retire(self._pending.pop(0))
+            if self._pinThread is not None:                    # nothing was ever flushed
+                self._pinThread.join()
+                self._pinThread = None
+            for fut in self._written:                          # the last two chunks; re-raises a writer's failure
+                if fut is not None:
+                    fut.result()
+            self._retirer.shutdown()
             self._writers.shutdown()
             self._stopPrefault = True
             for t in self._prefaulters:

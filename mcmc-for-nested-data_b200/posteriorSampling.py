@@ -18,6 +18,7 @@ ranks; sampling needs no communication.
 """
 
 import datetime
+import time
 import json
 import logging
 import os
@@ -114,6 +115,12 @@ def _sampleShard(rank, world, nChains, nIter, burn, thin, parameterName, nGroups
     lo, hi = (nChains * rank) // world, (nChains * (rank + 1)) // world
     myChains = hi - lo
     show = displayProgress and rank == 0
+    phases, mark = {}, [time.perf_counter()]
+
+    def phase(name):                                               # wall seconds of the call's phases, kept in lastRun
+        now = time.perf_counter()
+        phases[name] = phases.get(name, 0.0) + now - mark[0]
+        mark[0] = now
 
     eng = Engine(objective, nGroups, nResponsesPerGroup, pooling, myChains,
                  priorDistribution=priorDistribution, chainId0=lo,
@@ -122,9 +129,11 @@ def _sampleShard(rank, world, nChains, nIter, burn, thin, parameterName, nGroups
                     for c in range(lo, hi)] if myChains <= 64 else []
     if pooling == "partial" and priorDistribution is not None:
         logger.info("Partial pooling ignores prior distribution.")  # :713-714
+    phase("engine")
     _progress(logger, show, "Started looking for a reasonable starting state.")
     eng.initialise(parameterName, startingPointValueRange, startWithMLE, logger)
     _progress(logger, show, "Found a reasonable starting state.")
+    phase("start_state")
 
     retained = retainedIterations(nIter, burn, thin)
     nValues = len(retained) * eng.nCol * nChains
@@ -156,6 +165,7 @@ def _sampleShard(rank, world, nChains, nIter, burn, thin, parameterName, nGroups
     loggingInterval = int(numpy.round(nIter / 10.))
     if loggingInterval > 0:
         stops.update(range(loggingInterval, nIter, loggingInterval))
+    phase("store")
     loopStart = datetime.datetime.now()
     _progress(logger, show, r"Sampling started. 0% complete.")
     cur = 0
@@ -173,8 +183,10 @@ def _sampleShard(rank, world, nChains, nIter, burn, thin, parameterName, nGroups
     _progress(logger, show, "100%% complete. Elapsed Time: %s."
               % datetime.timedelta(seconds=int(elapsed.total_seconds())))
 
+    phase("sampling_loop")
     # ---- outputs
     store.finish()
+    phase("store_drain")
     header = sampleHeader(parameterName, eng.G, pooling)
     if useCsv:
         rows = store.hostArray()                                    # [rows][ncol][myChains]
@@ -186,11 +198,13 @@ def _sampleShard(rank, world, nChains, nIter, burn, thin, parameterName, nGroups
                 % (lo + c, datetime.timedelta(seconds=int(elapsed.total_seconds()))))
     global lastRun
     lastRun = {"engine": eng, "store": store, "retained": retained, "chains": (lo, hi),
-               "sampling_seconds": elapsed.total_seconds(), "store_device_bytes": store.deviceBytes}
+               "sampling_seconds": elapsed.total_seconds(), "store_device_bytes": store.deviceBytes,
+               "phases": phases}
     _barrier(world)                                                 # every shard file is complete
     if not useCsv and rank == 0:
         writeManifest(sampleDirectory, header, retained, nChains, world, pooling,
                       "float64" if storeDtype == torch.float64 else "float32")
+    phase("files")
     return elapsed
 
 
