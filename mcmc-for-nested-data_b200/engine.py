@@ -13,6 +13,7 @@ import ctypes
 import os
 import math
 import threading
+import time
 
 import numpy
 import scipy.special
@@ -154,12 +155,15 @@ class SampleStore(object):
     """
 
     def __init__(self, engine, nRows, dtype=torch.float64, path=None, logLikelihood=False, logLikSink=None,
-                 chunkBytes=128 << 20):
+                 chunkBytes=128 << 20, parts=1):
         self.engine = engine
         self.nRows = int(nRows)
         self.dtype = dtype
         self.iterations = []
         self._stopPrefault = False
+        self.waitedForWriters = 0.0                 # seconds the launching thread stood waiting for a pinned slot
+        self.retireWaitedForDevice = 0.0            # seconds the retire thread waited for chunks to leave the device
+        self.retireWrote = 0.0                      # seconds it spent writing them into the file(s)
         self.path = path
         self.streamed = path is not None
         self.logLikSink = logLikSink
@@ -199,8 +203,15 @@ class SampleStore(object):
             self._writers = concurrent.futures.ThreadPoolExecutor(max_workers=WRITER_THREADS)
             self._retirer = concurrent.futures.ThreadPoolExecutor(max_workers=1)     # one thread: chunks retire in order
             npdt = numpy.float64 if dtype == torch.float64 else numpy.float32
-            self.sink = numpy.lib.format.open_memmap(path, mode="w+", dtype=npdt,
-                                                     shape=(self.nRows, engine.nCol, engine.nChains))
+            # ``parts`` files, each [nRows][ncol][a contiguous range of the chains]: a tmpfs file's pages are
+            # allocated at 8 GB/s however many threads ask (measured on the GPU box, tools/store_populate_probe.py:
+            # 8.3 GB/s for one file, 16.3 for two, 17.8 for four).  An option for stores whose populating threads
+            # cannot stay ahead of the writers; one file by default (at config 3 it made no difference)
+            parts = int(max(1, min(parts, engine.nChains)))
+            self.partChains = [((engine.nChains * k) // parts, (engine.nChains * (k + 1)) // parts) for k in range(parts)]
+            self.partFiles = [path] if parts == 1 else [path[:-4] + ".part%d.npy" % k for k in range(parts)]
+            self.sinks = [numpy.lib.format.open_memmap(f, mode="w+", dtype=npdt, shape=(self.nRows, engine.nCol, c1 - c0))
+                          for f, (c0, c1) in zip(self.partFiles, self.partChains)]
             self._prefaulters = [threading.Thread(target=self._prefault, args=(k, PREFAULT_THREADS), daemon=True)
                                  for k in range(PREFAULT_THREADS)]
             for t in self._prefaulters:
@@ -215,9 +226,14 @@ class SampleStore(object):
         try:
             libc = ctypes.CDLL(None, use_errno=True)
             page = os.sysconf("SC_PAGE_SIZE")
-            addr = self.sink.ctypes.data
+            nParts = len(self.sinks)
+            if k >= nParts * (nThreads // nParts) and nThreads >= nParts:
+                return                                              # threads beyond an even share per file
+            sink = self.sinks[k % nParts]                           # this thread's file; its rank among that file's threads
+            k, nThreads = k // nParts, max(1, nThreads // nParts)
+            addr = sink.ctypes.data
             lo = addr - addr % page
-            end = addr + self.sink.nbytes
+            end = addr + sink.nbytes
             step = 64 << 20
             lo += k * step
             while lo < end and not self._stopPrefault:
@@ -261,7 +277,9 @@ class SampleStore(object):
             if self._pin is None:
                 raise RuntimeError("could not allocate the pinned staging buffers of the sample store")
         if self._written[c] is not None:            # pinned slot c still being written to the file: a whole ring behind
+            t0 = time.perf_counter()
             self._written[c].result()               # (re-raises what the retire thread raised)
+            self.waitedForWriters += time.perf_counter() - t0
         main = torch.cuda.current_stream(self.engine.device)
         filled = torch.cuda.Event()
         filled.record(main)
@@ -282,7 +300,10 @@ class SampleStore(object):
 
     def _retire(self, item):
         c, n, row0, copied = item
+        t0 = time.perf_counter()
         copied.synchronize()
+        t1 = time.perf_counter()
+        self.retireWaitedForDevice += t1 - t0
         nC = self.engine.nChains
         src = self._pin[c][:n].numpy()
         # pinned memory -> the file's pages on WRITER_THREADS host threads (numpy copies release the GIL; one
@@ -295,13 +316,15 @@ class SampleStore(object):
 
         def put(job):
             r, k0, k1 = job
-            self.sink[row0 + r, k0:k1] = src[r, k0:k1, :nC]
+            for sink, (c0, c1) in zip(self.sinks, self.partChains):
+                sink[row0 + r, k0:k1] = src[r, k0:k1, c0:c1]
         if len(jobs) > 1:
             list(self._writers.map(put, jobs))
         else:
             put(jobs[0])
         if self.logLik is not None and self.logLikSink is not None:
             self.logLikSink(row0, self._pinLL[c][:n].numpy()[:, :, :nC])
+        self.retireWrote += time.perf_counter() - t1
 
     def finish(self):
         """Drain the ring and close the file (streamed), or hand the log-likelihood rows over (resident)."""
@@ -318,7 +341,8 @@ class SampleStore(object):
             self._stopPrefault = True
             for t in self._prefaulters:
                 t.join()
-            self.sink.flush()
+            for sink in self.sinks:
+                sink.flush()
         elif self.logLik is not None and self.logLikSink is not None:
             n = len(self.iterations)
             if n:
@@ -327,7 +351,8 @@ class SampleStore(object):
     def hostArray(self):
         """[rows][ncol][nChains] numpy array (the file's memmap when streamed, after finish())."""
         if self.streamed:
-            return self.sink[:len(self.iterations)]
+            n = len(self.iterations)
+            return self.sinks[0][:n] if len(self.sinks) == 1 else numpy.concatenate([sk[:n] for sk in self.sinks], axis=2)
         return self.tensor[:len(self.iterations), :, :self.engine.nChains].cpu().numpy()
 
 

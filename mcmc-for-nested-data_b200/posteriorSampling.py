@@ -37,6 +37,8 @@ LOGLIK_VALUE_LIMIT = int(os.environ.get("MCMCN_LOGLIK_LIMIT", 200000000))
 # the binary store keeps the chains' FP64 values; "float32" (6e-8 relative, below the reference's "%f"
 # for |values| < 16) is an explicit opt-in that the manifest records
 STORE_DTYPE = os.environ.get("MCMCN_STORE_DTYPE", "float64")
+# files a single process writes its binary store as, by chain range (samples.part<k>.npy when more than one)
+STORE_PARTS = 1
 
 
 def samplePosterior(nChains, nIter, nSamples,
@@ -156,9 +158,14 @@ def _sampleShard(rank, world, nChains, nIter, burn, thin, parameterName, nGroups
     if not useCsv and STORE_DTYPE == "float32":
         storeDtype = torch.float32
     shardFile = "samples.npy" if world == 1 else "samples.rank%d.npy" % rank
+    # MCMCN_STORE_PARTS=k: a single process writes its store as k files by chain range (engine.SampleStore: a tmpfs
+    # file's pages are allocated at a fixed rate per file).  Off by default: at config 3 the writers are not what
+    # the sampling loop waits for (retire thread: 1.2 s writing, 1.7 s waiting for the device), measured both ways.
+    parts = int(os.environ.get("MCMCN_STORE_PARTS", STORE_PARTS))
     store = SampleStore(eng, max(len(retained), 1), storeDtype,
                         path=None if useCsv else os.path.join(sampleDirectory, shardFile),
-                        logLikelihood=bool(saveLogLikelihood), logLikSink=appendLogLikelihood)
+                        logLikelihood=bool(saveLogLikelihood), logLikSink=appendLogLikelihood,
+                        parts=parts if world == 1 else 1)
 
     # ---- Sampler._loop (:862-896): one call per progress mark; the store splits it where a chunk is full
     stops = set([nIter])
@@ -184,6 +191,9 @@ def _sampleShard(rank, world, nChains, nIter, burn, thin, parameterName, nGroups
               % datetime.timedelta(seconds=int(elapsed.total_seconds())))
 
     phase("sampling_loop")
+    phases["waited_for_store_writers"] = store.waitedForWriters     # part of the sampling loop
+    phases["retire_waited_for_device"] = store.retireWaitedForDevice
+    phases["retire_wrote"] = store.retireWrote
     # ---- outputs
     store.finish()
     phase("store_drain")
@@ -202,8 +212,10 @@ def _sampleShard(rank, world, nChains, nIter, burn, thin, parameterName, nGroups
                "phases": phases}
     _barrier(world)                                                 # every shard file is complete
     if not useCsv and rank == 0:
+        parted = [{"file": os.path.basename(f), "chains": [int(c0), int(c1)]}
+                  for f, (c0, c1) in zip(store.partFiles, store.partChains)] if world == 1 else None
         writeManifest(sampleDirectory, header, retained, nChains, world, pooling,
-                      "float64" if storeDtype == torch.float64 else "float32")
+                      "float64" if storeDtype == torch.float64 else "float32", shards=parted)
     phase("files")
     return elapsed
 
@@ -235,13 +247,15 @@ def writeSampleCsv(path, chain, header, iterations, rows):
             h.write("\n")
 
 
-def writeManifest(sampleDirectory, header, iterations, nChains, world, pooling, dtype):
+def writeManifest(sampleDirectory, header, iterations, nChains, world, pooling, dtype, shards=None):
     """``sample/manifest.json``: what sampleDiagnosis.openSamples reads.  One shard file per rank, each
-    [rows][columns][chains of that rank] (.npy), chains split contiguously over the ranks."""
-    shards = []
-    for r in range(world):
-        lo, hi = (nChains * r) // world, (nChains * (r + 1)) // world
-        shards.append({"file": "samples.npy" if world == 1 else "samples.rank%d.npy" % r, "chains": [lo, hi]})
+    [rows][columns][chains of that rank] (.npy), chains split contiguously over the ranks; a single process
+    names its own file(s) (``shards``: one, or two by chain range for a large store)."""
+    if shards is None:
+        shards = []
+        for r in range(world):
+            lo, hi = (nChains * r) // world, (nChains * (r + 1)) // world
+            shards.append({"file": "samples.npy" if world == 1 else "samples.rank%d.npy" % r, "chains": [lo, hi]})
     man = {"format": "mcmcn-samples-2", "header": list(header), "iterations": list(map(int, iterations)),
            "nChains": int(nChains), "pooling": pooling, "dtype": dtype,
            "layout": "[rows][columns][chains]", "shards": shards}

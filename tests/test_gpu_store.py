@@ -58,6 +58,39 @@ def test_streamed_store_equals_resident_store(dtype, tmp_path):
     assert got["streamed"][1].shape == (nRows, 120, 37) and numpy.isfinite(got["streamed"][1]).all()
 
 
+def test_store_in_two_files_by_chain_range_equals_one_file(tmp_path, monkeypatch):
+    """A single-process store written as two files by chain range (an option: a tmpfs file's pages are allocated at
+    a fixed rate per file): the same rows land in samples.part0/1.npy, the manifest names both with their chain
+    ranges, and loadSamples / Diagnostic over the two files equal those over the one file."""
+    import posteriorSampling as ps
+    import sampleDiagnosis as sd
+    from objectives import Objective
+    obj, names, nResp, ranges = parity.syntheticRegression(G=5, R=12, K=2)
+    handle = Objective.linear_regression(obj.X, obj.y)
+    args = (7, 300, 60, names, 5, nResp, "partial", handle)
+    kw = dict(saveLogLikelihood=False, startingPointValueRange=ranges, displayProgress=False)
+    monkeypatch.setattr(ps, "CSV_VALUE_LIMIT", 0)
+    ps.samplePosterior(*args, str(tmp_path / "one"), **kw)
+    assert os.path.exists(str(tmp_path / "one/sample/samples.npy"))
+    monkeypatch.setattr(ps, "STORE_PARTS", 2)
+    ps.samplePosterior(*args, str(tmp_path / "two"), **kw)
+    man = json.load(open(str(tmp_path / "two/sample/manifest.json")))
+    assert man["shards"] == [{"file": "samples.part0.npy", "chains": [0, 3]}, {"file": "samples.part1.npy", "chains": [3, 7]}]
+    assert not os.path.exists(str(tmp_path / "two/sample/samples.npy"))
+    whole = numpy.load(str(tmp_path / "one/sample/samples.npy"))
+    numpy.testing.assert_array_equal(numpy.load(str(tmp_path / "two/sample/samples.part0.npy")), whole[:, :, :3])
+    numpy.testing.assert_array_equal(numpy.load(str(tmp_path / "two/sample/samples.part1.npy")), whole[:, :, 3:])
+    numpy.testing.assert_array_equal(ps.lastRun["store"].hostArray(), whole)
+    k1, a1, c1 = sd.loadSamples(str(tmp_path / "one/sample/"))
+    k2, a2, c2 = sd.loadSamples(str(tmp_path / "two/sample/"))
+    assert k1 == k2 and c1 == c2 == list(range(7))
+    numpy.testing.assert_array_equal(a1, a2)
+    d1, d2 = sd.Diagnostic(str(tmp_path / "one/sample/")), sd.Diagnostic(str(tmp_path / "two/sample/"))
+    for k in k1:
+        assert d1.rhat[k] == d2.rhat[k] and d1.effectiveN[k] == d2.effectiveN[k]
+        assert d1.median[k] == d2.median[k] and d1.hdi[k] == d2.hdi[k]
+
+
 def test_samplePosterior_binary_store_manifest_and_slabbed_diagnostics(tmp_path, monkeypatch, capsys):
     """samplePosterior forced into the binary store (FP64 by default, several ring chunks): same draws
     as the CSV run (which rounds them to 1e-6 with "%f"); Diagnostic / diagnoseSamples over the memory-mapped
