@@ -46,7 +46,7 @@ static cudaError_t launch_sweep(sweep_fn fn, dim3 grid, dim3 block, size_t smem,
 static const KernelSet* find_set(int objective, int P, int K, int precision) {
     typedef const KernelSet* (*getter)(int*);
     static const getter getters[] = {sets_linreg_a, sets_linreg_b, sets_linreg_c, sets_linreg_d, sets_linreg_e,
-                                     sets_linreg_f, sets_linreg_g, sets_linreg_h, sets_linreg_i, sets_logit, sets_gauss};
+                                     sets_linreg_f, sets_linreg_g, sets_linreg_h, sets_linreg_i, sets_logit, sets_gauss, sets_gauss_b};
     for (getter get : getters) {
         int n = 0;
         const KernelSet* sets = get(&n);

@@ -40,6 +40,7 @@ const KernelSet* sets_linreg_h(int* n);
 const KernelSet* sets_linreg_i(int* n);
 const KernelSet* sets_logit(int* n);
 const KernelSet* sets_gauss(int* n);
+const KernelSet* sets_gauss_b(int* n);
 sweep_fn tc_sweep_kernel(int f, bool uniform208, int k_blocks);    // mcmcn_sets_tc.cu (one K block), mcmcn_sets_tc2.cu (two)
 sweep_fn tc_sweep_kernel_two_blocks(int f);
 typedef void (*eval_tc_fn)(const EvalTcArgs);

@@ -275,6 +275,28 @@ def test_replay_bernoulli_logit(pooling):
     assert ties64 == 0
 
 
+@pytest.mark.parametrize("P,pooling", [(5, "partial"), (8, "partial"), (6, "none"), (7, "complete")])
+def test_replay_gaussian_distribution_with_5_to_8_parameters(P, pooling):
+    """The Gaussian-distribution objective (example/distribution.py:18-24) beyond the example's own sizes: 5..8
+    parameters (GaussDist<5..8>, csrc/mcmcn_sets_gauss_b.cu), ragged groups, all three pooling modes."""
+    rs = numpy.random.RandomState(100 + P)
+    G = 9
+    nResp = [int(v) for v in rs.randint(3, 12, size=G)]
+    mu = rs.normal(0, 2, size=(P, G))
+    sd = rs.uniform(0.5, 2.0, size=P)
+    obj = parity.po.GaussianDistributionObjective(mu, sd, nResp)
+    names = tuple("m%d" % j for j in range(P))
+    ranges = dict((n, [-3, 3]) for n in names)
+    prior = None if pooling == "partial" else [scipy.stats.norm(0, 10)] * P
+    res64 = parity.replay(obj, names, G, nResp, pooling, prior, ranges, nChains=3, nIter=90, nSamples=30,
+                          precision="fp64", force=False)
+    err64, ties64 = parity.checkReplay(res64, 1e-11, 0.0)
+    assert ties64 == 0
+    numpy.testing.assert_allclose(res64.rows, res64.oracleRows, rtol=1e-9, atol=1e-9)
+    res = parity.replay(obj, names, G, nResp, pooling, prior, ranges, nChains=3, nIter=90, nSamples=30, precision="fp32")
+    parity.checkReplay(res, 1e-5, 1e-5)
+
+
 @pytest.mark.parametrize("objective", ["regression", "regression-8", "regression-12", "regression-fp32-pipe", "logit"])
 def test_replay_complete_pooling_split_over_observations(objective, monkeypatch):
     """Complete pooling at scale: the engine evaluates the single group of all N observations as

@@ -41,6 +41,10 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert lib.mcmcn_supported(nat.OBJ_LINEAR_REGRESSION, K + 1, K, 32) == 1
         assert lib.mcmcn_supported(nat.OBJ_LINEAR_REGRESSION, K + 1, K, 64) == 1
     assert lib.mcmcn_supported(nat.OBJ_LINEAR_REGRESSION, 18, 17, 32) == 0
+    for P in range(1, 9):                                                      # Gaussian distribution: 1..8 parameters
+        assert lib.mcmcn_supported(nat.OBJ_GAUSSIAN_DISTRIBUTION, P, 0, 32) == 1
+        assert lib.mcmcn_supported(nat.OBJ_GAUSSIAN_DISTRIBUTION, P, 0, 64) == 1
+    assert lib.mcmcn_supported(nat.OBJ_GAUSSIAN_DISTRIBUTION, 9, 0, 32) == 0
 
 
 def test_ctypes_structs_mirror_the_header(tmp_path):
