@@ -311,6 +311,20 @@ __device__ __forceinline__ float lo2(f32x2 v) {
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
     return lo;
 }
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// four consecutive floats (16-byte aligned) as two packed pairs: one 128-bit load, the pairs are its registers
+__device__ __forceinline__ void load_pairs(const float* p, f32x2& a, f32x2& b) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p);
+    a = v.x;
+    b = v.y;
+}
 __device__ __forceinline__ float sum2(f32x2 v) {
     float lo, hi;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
@@ -470,6 +484,9 @@ __device__ __forceinline__ double softplus_t(double eta) {
 #ifndef MCMCN_LOGIT_FOLD_QUADS
 #define MCMCN_LOGIT_FOLD_QUADS 16
 #endif
+#ifndef MCMCN_LOGIT_PAIRS
+#define MCMCN_LOGIT_PAIRS 1
+#endif
 struct Logit {
     static constexpr int P = 2;
     static constexpr int UNIT = 8;
@@ -506,6 +523,96 @@ struct Logit {
     // each), and four FFMA (e; product *= 1 + t; two for the linear part) instead of seven FP32 ops.
     // The product of 16 factors carries 16 roundings of 6e-8 relative, i.e. the same absolute error
     // in the logarithm as the sum of 16 rounded logarithms had.
+#if MCMCN_LOGIT_PAIRS
+    // Production form of the loop above: the same four FMAs and one ex2 per evaluation, issued for TWO
+    // observations of one chain at a time as packed FFMA2 (e; product *= 1 + t; s += (y - 1/2) e), the pair
+    // (x_j, x_j+1) being an aligned register pair of the 128-bit shared load as it is; only the |e| / 2 term
+    // stays scalar (no |.| modifier on packed operands).  7 instructions per two evaluations instead of 10:
+    // the loop is bound by the MUFU pipe (8 clk per warp and ex2), and the fewer issue slots the FMAs take,
+    // the closer the three resident warps per scheduler keep that pipe to busy.  Even and odd observations
+    // carry their own product and sum; the fold multiplies / adds the two halves before the one lg2.
+    template <int C>
+    __device__ static __forceinline__ void all_obs(const float* __restrict__ blk, int nobs, const Work<C, float>& w, double (&acc)[C]) {
+        const int nq = nobs >> 2, rem = nobs & 3;
+        f32x2 aa[C], bb[C], s2[C], pr2[C];
+        const f32x2 one2 = pack2(1.0f, 1.0f), mhalf2 = pack2(-0.5f, -0.5f);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float a = w.th[c][0] * 1.4426950408889634f, b = w.th[c][1] * 1.4426950408889634f;
+            aa[c] = pack2(a, a);
+            bb[c] = pack2(b, b);
+            s2[c] = 0ull;
+            pr2[c] = one2;
+        }
+#define MCMCN_LOGIT_PAIR(xp, yp)                                                         \
+        {                                                                                \
+            const f32x2 yh = fadd2((yp), mhalf2);                                        \
+            _Pragma("unroll") for (int c = 0; c < C; ++c) {                              \
+                const f32x2 e2 = ffma2(bb[c], (xp), aa[c]);                              \
+                float e0, e1, t0, t1, s0, s1;                                            \
+                unpack2(e2, e0, e1);                                                     \
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(-fabsf(e0)));          \
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(-fabsf(e1)));          \
+                pr2[c] = ffma2(pr2[c], pack2(t0, t1), pr2[c]);                           \
+                unpack2(ffma2(yh, e2, s2[c]), s0, s1);                                   \
+                s2[c] = pack2(fmaf(-0.5f, fabsf(e0), s0), fmaf(-0.5f, fabsf(e1), s1));   \
+            }                                                                            \
+        }
+        // one observation: the even half only (the odd half keeps its product and sum)
+#define MCMCN_LOGIT_ONE(xv, yv)                                                          \
+        {                                                                                \
+            const float yh = (yv) - 0.5f;                                                \
+            _Pragma("unroll") for (int c = 0; c < C; ++c) {                              \
+                float p0, p1, s0, s1, t;                                                 \
+                unpack2(pr2[c], p0, p1);                                                 \
+                unpack2(s2[c], s0, s1);                                                  \
+                const float e = fmaf(lo2(bb[c]), (xv), lo2(aa[c]));                      \
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(-fabsf(e)));            \
+                p0 = fmaf(p0, t, p0);                                                    \
+                s0 = fmaf(-0.5f, fabsf(e), fmaf(yh, e, s0));                             \
+                pr2[c] = pack2(p0, p1);                                                  \
+                s2[c] = pack2(s0, s1);                                                   \
+            }                                                                            \
+        }
+#define MCMCN_LOGIT_FOLD()                                                               \
+        _Pragma("unroll") for (int c = 0; c < C; ++c) {                                  \
+            float p0, p1, l;                                                             \
+            unpack2(pr2[c], p0, p1);                                                     \
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(p0 * p1));                  \
+            acc[c] += (double)(0.6931471805599453f * (sum2(s2[c]) - l));                 \
+            s2[c] = 0ull;                                                                \
+            pr2[c] = one2;                                                               \
+        }
+        // the 1-3 observations of the last, partial quad join the first fold
+        const float* xr = blk + (size_t)nq * UNIT;
+        if (rem & 2) MCMCN_LOGIT_PAIR(pack2(xr[0], xr[1]), pack2(xr[4], xr[5]))
+        if (rem & 1) MCMCN_LOGIT_ONE(xr[rem - 1], xr[4 + rem - 1])
+        // MCMCN_LOGIT_FOLD_QUADS quads per fold: one lg2 and one FP32 -> FP64 conversion (both XU operations) per
+        // fold and chain.  16 quads: each half's product of up to 34 factors in (1, 2] and the product of the two
+        // halves stay below 2^67; their roundings (4e-6 relative) move the logarithm by 6e-6 absolute -- against
+        // group log-likelihoods of tens, inside the 1e-5 relative bar with a wide margin.
+        for (int q0 = 0; q0 < nq; q0 += MCMCN_LOGIT_FOLD_QUADS) {
+            const int qend = min(nq, q0 + MCMCN_LOGIT_FOLD_QUADS);
+            for (int q1 = q0; q1 < qend; q1 += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (q1 + u < qend) {
+                        f32x2 xa, xb, ya, yb;
+                        load_pairs(blk + (size_t)(q1 + u) * UNIT, xa, xb);
+                        load_pairs(blk + (size_t)(q1 + u) * UNIT + 4, ya, yb);
+                        MCMCN_LOGIT_PAIR(xa, ya)
+                        MCMCN_LOGIT_PAIR(xb, yb)
+                    }
+                }
+            }
+            MCMCN_LOGIT_FOLD()
+        }
+        if (nq == 0) MCMCN_LOGIT_FOLD()
+#undef MCMCN_LOGIT_PAIR
+#undef MCMCN_LOGIT_ONE
+#undef MCMCN_LOGIT_FOLD
+    }
+#else
     template <int C>
     __device__ static __forceinline__ void all_obs(const float* __restrict__ blk, int nobs, const Work<C, float>& w, double (&acc)[C]) {
         const int nq = nobs >> 2, rem = nobs & 3;
@@ -564,6 +671,7 @@ struct Logit {
 #undef MCMCN_LOGIT_OBS
 #undef MCMCN_LOGIT_FOLD
     }
+#endif
     template <int C>
     __device__ static __forceinline__ void all_obs(const double* __restrict__ blk, int nobs, const Work<C, double>& w, double (&acc)[C]) {
         const int nq = nobs >> 2, rem = nobs & 3;

@@ -699,8 +699,10 @@ class Summary(object):
 
 
 def diagnoseSamples(outputDirectory, assessConvergence=True, printSummary=True, nFigures=10):
-    """Diagnose samples (sampleDiagnosis.py:11-85).  Same files and stdout as the reference;
-    ``nFigures`` is accepted for compatibility but figures are not produced.  Under torch.distributed
+    """Diagnose samples (sampleDiagnosis.py:11-85).  Same files and stdout as the reference; with
+    ``nFigures`` > 0 also ``figure/logLikelihood.png``, ``figure/traceplot/traceplot<suffix>.png`` and
+    ``figure/bivariate/bivariate<suffix>.png`` for the first nFigures key suffices (:73-85; figures.py
+    rasterises them itself).  Under torch.distributed
     with the binary store sharded one file per rank, every rank reduces its own chains (Diagnostic /
     Summary exchange what they must) and rank 0 alone writes and prints."""
     sampleDirectory = outputDirectory + "/sample/"
@@ -732,9 +734,25 @@ def diagnoseSamples(outputDirectory, assessConvergence=True, printSummary=True, 
         if speaks:
             summary.print(sampleDirectory + "/summary.csv")
             summary.print(None)
-    # figures (Figure, :494-759) are out of scope for the GPU engine
+
+    if nFigures > 0 and speaks:                                    # :73-85
+        traceplotDirectory = outputDirectory + "/figure/traceplot/"
+        bivariateDirectory = outputDirectory + "/figure/bivariate/"
+        for directory in (traceplotDirectory, bivariateDirectory):
+            os.makedirs(directory, exist_ok=True)
+        fig = Figure(sampleDirectory)
+        fig.loglikelihood(outputDirectory + "/figure/logLikelihood.png")
+        fig.traceplots(traceplotDirectory, nFigures)
+        fig.bivariates(bivariateDirectory, nFigures)
 
 
 def _stdout_csv(content):
     """Tab-indented, comma-spaced echo of a CSV text (:762-763)."""
     print("\t" + "\n\t".join(line.replace(",", ", ") for line in content.split("\n")))
+
+
+def Figure(sampleDirectory, source=None):
+    """The reference's ``Figure`` (sampleDiagnosis.py:494-759): ``loglikelihood``, ``traceplots``, ``traceplot``,
+    ``bivariates``, ``bivariate`` with its file names; implemented in figures.py."""
+    import figures
+    return figures.Figure(sampleDirectory, source=source)

@@ -66,6 +66,26 @@ def test_diagnoseSamples_writes_the_reference_files(case, tmp_path, capsys):
     assert printed == open(goldenPath(case, "diagnose.stdout.txt")).read()
 
 
+def test_diagnoseSamples_writes_the_figures(tmp_path, capsys):
+    """nFigures > 0 (:73-85): the tables as before, then figure/logLikelihood.png and one trace plot and one
+    bivariate plot per key suffix, hyper-parameters first."""
+    import figures
+    import sampleDiagnosis as sd
+    case = "c1_distribution_partial"
+    out = _stage(case, tmp_path)
+    shutil.copy(os.path.join(GOLDEN, case, "logLikelihood.0.csv"), os.path.join(out, "sample"))
+    sd.diagnoseSamples(out, nFigures=2)
+    printed = capsys.readouterr().out
+    tables = open(goldenPath(case, "diagnose.stdout.txt")).read()
+    assert printed.startswith(tables)
+    assert "Creating loglikelihood plot: Done" in printed[len(tables):] and printed.rstrip().endswith("Creating bivariate plots: Done.")
+    assert sorted(os.listdir(out + "/figure/traceplot")) == ["traceplot[000].png", "traceplot_.png"]
+    assert sorted(os.listdir(out + "/figure/bivariate")) == ["bivariate[000].png", "bivariate_.png"]
+    assert figures.readPng(out + "/figure/logLikelihood.png").shape == (300, 1200, 3)
+    img = figures.readPng(out + "/figure/traceplot/traceplot_.png")
+    assert img.shape == (1200, 1200, 3) and (img != 255).any()
+
+
 def test_computeHpdInterval_matches_reference_formula():
     import sampleDiagnosis as sd
     rs = numpy.random.RandomState(3)
