@@ -484,6 +484,12 @@ __device__ __forceinline__ double softplus_t(double eta) {
 #ifndef MCMCN_LOGIT_FOLD_QUADS
 #define MCMCN_LOGIT_FOLD_QUADS 16
 #endif
+#ifndef MCMCN_HYPER_EARLY_DRAWS
+#define MCMCN_HYPER_EARLY_DRAWS 0
+#endif
+#ifndef MCMCN_PREFETCH_NEXT_GROUP
+#define MCMCN_PREFETCH_NEXT_GROUP 0
+#endif
 #ifndef MCMCN_LOGIT_PAIRS
 #define MCMCN_LOGIT_PAIRS 1
 #endif
@@ -997,8 +1003,25 @@ __global__ void __launch_bounds__(MAXT, MINB) sweep_kernel(const SweepArgs a) {
                             prefetch_l1(a.hyper + ((size_t)3 * P + p + 1) * S + chl[c]);
                             prefetch_l1(a.hyper + ((size_t)4 * P + p + 1) * S + chl[c]);
                         }
+#if MCMCN_PREFETCH_NEXT_GROUP
+                        else prefetch_l1(a.lprior + row + (size_t)a.G * S + chl[c]);
+#endif
                     }
                 }
+#if MCMCN_PREFETCH_NEXT_GROUP
+                else if (g + 1 < g1) {                                 // last sweep of the group: the next group's state, which
+#pragma unroll                                                         // the group prologue and its first sweep read, into L1
+                    for (int c = 0; c < C; ++c) {
+                        const size_t nx = (size_t)(g + 1) * S + chl[c];
+#pragma unroll
+                        for (int q = 0; q < P; ++q) prefetch_l1(a.theta + (size_t)q * a.G * S + nx);
+                        prefetch_l1(a.scale + nx);
+                        prefetch_l1(a.ll + nx);
+                        if (count) prefetch_l1(a.counts + nx);
+                        if (!partial) prefetch_l1(a.lprior + nx);
+                    }
+                }
+#endif
                 if (replay) {
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
@@ -1364,6 +1387,19 @@ __global__ void __launch_bounds__(CX * (MCMCN_HYPER_SLICES / SPR)) hyper_onepass
         c = a.hyper[((size_t)0 * a.P + p) * S + ch];
         if (!finite64(c)) c = th[0];
     }
+#if MCMCN_HYPER_EARLY_DRAWS
+    // The two random draws of this (name, chain) do not depend on the sums: the finishing row forms them before
+    // its loads, under the other rows' memory latency, instead of after the block's barrier (a serial tail of
+    // Philox, Box-Muller, Marsaglia-Tsang and FP64 logarithms with the rest of the GPU idle).
+    double z_early = 0.0, q_early = 0.0;
+    if (ty == 0 && on) {
+        if (!a.tape_zmu) {
+            const uint4 r = philox_draw(a.chain_id0 + ch, a.seed, a.iter, MCMCN_STREAM_HYPER, (unsigned)p, 0u);
+            z_early = normal_from(r.x, r.y);
+        }
+        if (!a.tape_qsig) q_early = 1.0 / gamma_draw((n - 1.0) / 2.0, a.chain_id0 + ch, a.seed, a.iter, (unsigned)p);
+    }
+#endif
 #pragma unroll
     for (int q = 0; q < SPR; ++q) {
         const int slice = ty * SPR + q;
@@ -1406,8 +1442,12 @@ __global__ void __launch_bounds__(CX * (MCMCN_HYPER_SLICES / SPR)) hyper_onepass
         double z;
         if (a.tape_zmu) z = a.tape_zmu[(size_t)p * S + ch];
         else {
+#if MCMCN_HYPER_EARLY_DRAWS
+            z = z_early;
+#else
             const uint4 r = philox_draw(a.chain_id0 + ch, a.seed, a.iter, MCMCN_STREAM_HYPER, (unsigned)p, 0u);
             z = normal_from(r.x, r.y);
+#endif
         }
         const double mu = __dadd_rn(muHat, __dmul_rn(sdm, z));                    // :487
         const double dmu = mu - muHat;
@@ -1416,7 +1456,11 @@ __global__ void __launch_bounds__(CX * (MCMCN_HYPER_SLICES / SPR)) hyper_onepass
         const double aa = (n - 1.0) / 2.0;
         double q;                                                                 // unit inverse-gamma draw, :497-498
         if (a.tape_qsig) q = a.tape_qsig[(size_t)p * S + ch];
+#if MCMCN_HYPER_EARLY_DRAWS
+        else q = q_early;
+#else
         else q = 1.0 / gamma_draw(aa, a.chain_id0 + ch, a.seed, a.iter, (unsigned)p);
+#endif
         const double sigma2 = __dadd_rn(__dmul_rn(q, __dmul_rn(aa, hat)), 0.0);
         const double sd = sqrt(sigma2);
         a.hyper[((size_t)0 * a.P + p) * S + ch] = mu;

@@ -396,6 +396,9 @@ class Engine(object):
             raise ValueError("partial pooling needs at least 2 groups (the reference divides by nGroups - 1)")
 
         # ---- model
+        # MCMCN_TASK_OBS: observations per task of the FP32-pipe step kernel (a CTA's run of consecutive groups,
+        # staged by one TMA copy); results do not depend on it -- a tuning knob for experiments
+        taskObsTarget = int(os.environ.get("MCMCN_TASK_OBS", taskObsTarget))
         m, keep = self._buildModel(stepped, pooling, taskObsTarget, tensorCore=True)
         (self._data, self._group_off, self._group_nobs, self._task_group0, self._obj_const, self._tc_data,
          self._tc_group_off, self._group_off_h, self._task_group0_h) = keep
