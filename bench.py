@@ -294,7 +294,7 @@ def roofline(args, tensorCore, sweepMs, chains, peakFp32, peakTf32, peakMufu):
         evals = 2.0 * G * R * chains
         perEval = 1.0 + float(-(-R // 64)) / R                      # one ex2 per observation, one lg2 per fold of 64
         executed = perEval * evals / (sweepMs * 1e-3)
-        return {"bound": "mufu", "kernel": "sweep_kernel<Logit,4,float>", "achieved": executed / 1e9, "peak": peakMufu / 1e9,
+        return {"bound": "mufu", "kernel": "sweep_kernel<Logit,2,float>", "achieved": executed / 1e9, "peak": peakMufu / 1e9,
                 "unit": "Gop/s", "frac": executed / peakMufu, "mufu_executed_per_eval": perEval,
                 "frac_at_survey_2_mufu_per_eval": 2.0 * evals / (sweepMs * 1e-3) / peakMufu,
                 "traffic": TRAFFIC["c5"][0] * chains / 4096.0, "traffic_source": TRAFFIC["c5"][1],

@@ -27,6 +27,18 @@ namespace mcmcn {
 
 #define MCMCN_LOG_SQRT_2PI 0.91893853320467274178  /* numpy.log(numpy.sqrt(2*numpy.pi)) */
 
+// Build switches, each the kept side of a measured A/B (tools/variant.sh builds the other side; results are
+// bit-identical either way except MCMCN_LOGIT_PAIRS, which reorders the FP32 sums of the logit loop):
+#ifndef MCMCN_HYPER_EARLY_DRAWS
+#define MCMCN_HYPER_EARLY_DRAWS 1      /* one-pass Gibbs kernel: the two draws before the sums (18.3 -> 16.9 us at config 3) */
+#endif
+#ifndef MCMCN_PREFETCH_NEXT_GROUP
+#define MCMCN_PREFETCH_NEXT_GROUP 1    /* FP32-pipe step kernel: next group's state and next sweep's log-prior into L1 */
+#endif
+#ifndef MCMCN_LOGIT_PAIRS
+#define MCMCN_LOGIT_PAIRS 1            /* Bernoulli-logit loop as packed FFMA2 over observation pairs */
+#endif
+
 // ---------------------------------------------------------------- small PTX helpers
 __device__ __forceinline__ unsigned smem_u32(const void* p) {
     return (unsigned)__cvta_generic_to_shared(p);
@@ -483,15 +495,6 @@ __device__ __forceinline__ double softplus_t(double eta) {
 }
 #ifndef MCMCN_LOGIT_FOLD_QUADS
 #define MCMCN_LOGIT_FOLD_QUADS 16
-#endif
-#ifndef MCMCN_HYPER_EARLY_DRAWS
-#define MCMCN_HYPER_EARLY_DRAWS 0
-#endif
-#ifndef MCMCN_PREFETCH_NEXT_GROUP
-#define MCMCN_PREFETCH_NEXT_GROUP 0
-#endif
-#ifndef MCMCN_LOGIT_PAIRS
-#define MCMCN_LOGIT_PAIRS 1
 #endif
 struct Logit {
     static constexpr int P = 2;

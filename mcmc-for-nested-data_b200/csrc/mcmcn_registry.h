@@ -13,7 +13,7 @@ typedef void (*pointwise_fn)(const SweepArgs, const long long*, double*);
 struct KernelSet {
     int objective, P, K, precision;
     int c_wide;                 // chains per lane of the wide variant
-    sweep_fn sweep_fast[4];     // wide, production (128-thread CTAs, 3 per SM, 168 registers): index = MCMCN_F_PARTIAL | MCMCN_F_COUNT
+    sweep_fn sweep_fast[4];     // wide, production (128-thread CTAs, MB per SM): index = MCMCN_F_PARTIAL | MCMCN_F_COUNT
     sweep_fn sweep_wide;        // wide, general (replay tapes, traces, streamed groups)
     sweep_fn sweep_one;         // one chain per lane, general
     sweep_fn eval_wide, eval_one;
@@ -22,12 +22,16 @@ struct KernelSet {
     int park_doubles;           // shared-memory parking slots per chain (7 + Aux doubles)
 };
 
-#define MCMCN_SET(OBJ_ID, OBJ, KK, PREC, T, CW)                                                          \
+// MB = resident CTAs per SM the production variants are compiled for (__launch_bounds__(128, MB): 3 -> 168
+// registers, 8 -> 64).  The regression loop wants the registers (3); the Bernoulli-logit loop is short and its
+// decision phases are latency-bound, so it runs best with many resident warps (mcmcn_sets_logit.cu).
+#define MCMCN_SET_MB(OBJ_ID, OBJ, KK, PREC, T, CW, MB)                                                   \
     {OBJ_ID, OBJ::P, KK, PREC, CW,                                                                       \
-     {sweep_kernel<OBJ, CW, T, 3, 0, 128>, sweep_kernel<OBJ, CW, T, 3, 1, 128>,                          \
-      sweep_kernel<OBJ, CW, T, 3, 2, 128>, sweep_kernel<OBJ, CW, T, 3, 3, 128>},                         \
+     {sweep_kernel<OBJ, CW, T, MB, 0, 128>, sweep_kernel<OBJ, CW, T, MB, 1, 128>,                        \
+      sweep_kernel<OBJ, CW, T, MB, 2, 128>, sweep_kernel<OBJ, CW, T, MB, 3, 128>},                       \
      sweep_kernel<OBJ, CW, T, 2, -1>, sweep_kernel<OBJ, 1, T, 1, -1>,                                    \
      eval_kernel<OBJ, CW, T>, eval_kernel<OBJ, 1, T>, pointwise_kernel<OBJ, T>, (int)sizeof(T), 7 + OBJ::AUX_DOUBLES}
+#define MCMCN_SET(OBJ_ID, OBJ, KK, PREC, T, CW) MCMCN_SET_MB(OBJ_ID, OBJ, KK, PREC, T, CW, 3)
 
 const KernelSet* sets_linreg_a(int* n);
 const KernelSet* sets_linreg_b(int* n);

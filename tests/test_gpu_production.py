@@ -108,6 +108,31 @@ def test_production_logit_kernel_equals_general_bit_for_bit(pooling, monkeypatch
     _assertIdentical(prod, gen)
 
 
+def test_results_do_not_depend_on_the_task_size(monkeypatch):
+    """MCMCN_TASK_OBS (observations per CTA task of the FP32-pipe step kernel) is a tuning knob: a task is a run
+    of whole groups, a group's sum is formed by one thread either way."""
+    import torch
+    from engine import Engine
+    G, R, nC = 40, 50, 130
+    obj, names, nResp, ranges = parity.syntheticLogit(G=G, R=R)
+    states = []
+    for taskObs in (None, "50", "1000"):
+        if taskObs is None:
+            monkeypatch.delenv("MCMCN_TASK_OBS", raising=False)
+        else:
+            monkeypatch.setenv("MCMCN_TASK_OBS", taskObs)
+        eng = Engine(parity.deviceObjective(obj, nResp, "fp32"), G, nResp, "partial", nC, chainId0=3, seed=11)
+        eng.initialise(names, ranges)
+        eng.run(0, 120, 100, 2)
+        torch.cuda.synchronize()
+        states.append((eng.model.n_tasks, eng.getState()))
+    monkeypatch.delenv("MCMCN_TASK_OBS", raising=False)
+    assert states[1][0] == G and states[2][0] < states[0][0] < G          # one group per task ... many
+    for _, st in states[1:]:
+        for key in ("theta", "ll", "scale", "mu", "sigma2"):
+            assert (st[key] == states[0][1][key]).all(), key
+
+
 def test_production_kernels_with_many_groups_equal_general_bit_for_bit(monkeypatch):
     """G >= 512: the production run also takes hyper_onepass_kernel; MCMCN_GENERAL only swaps the
     step kernel, so both arms use the same Gibbs kernel and must agree bit for bit."""
