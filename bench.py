@@ -525,7 +525,7 @@ def fullRun(gpu, args, chainsTotal, nIter, nSamples, withDiagnostics):
            "chain_iterations_per_s": chainsTotal * nIter / wall,
            "store": {"dtype": args.store_dtype, "bytes_per_rank": int(rows * eng.nCol * myChains * elem),
                      "directory": base, "device_ring_bytes": int(run["store_device_bytes"]),
-                     "pinned_host_bytes": int(run["store_device_bytes"])},
+                     "pinned_host_bytes": int(run.get("store_pinned_bytes", run["store_device_bytes"]))},
            "phases_s": {k: round(v, 3) for k, v in run.get("phases", {}).items()},
            "h2d_bytes": h2d, "d2h_bytes": int(d2h)}
     if reduced is not None:

@@ -127,6 +127,10 @@ WRITER_THREADS = _hostThreads("MCMCN_STORE_THREADS")
 # as many as writers: the file's pages are populated while the chains burn in and the writers have nothing to do (C3:
 # 37.8 GB in 2.9 s takes eight threads; with four the writers met unpopulated pages and the sampling phase waited)
 PREFAULT_THREADS = int(os.environ.get("MCMCN_PREFAULT_THREADS", WRITER_THREADS))
+# pinned staging chunks of the streamed sample store (the device ring stays at two chunks).  Two: measured at config 3
+# (profiles/experiments/r2_store_pin_slots_ab.log), 4 and 6 slots leave the sampling loop where it is or slower (5.96-5.98 s
+# against 6.06-6.13 and 6.47): the launching thread's wait for a slot is only its run-ahead being throttled, not device idle time
+PIN_SLOTS = int(os.environ.get("MCMCN_STORE_PIN_SLOTS", "2"))
 
 
 def retainedCount(lo, hi, burn, thin):
@@ -145,8 +149,10 @@ class SampleStore(object):
         chains have filled one chunk it is copied to pinned host memory on a side stream while they
         fill the other, and then written into ``path``, a .npy file [nRows][ncol][nChains] opened with
         numpy.lib.format.open_memmap, by a retire thread (which waits for the copy and deals the rows to
-        the writer threads) -- the thread that launches the kernels only waits if the writers are a whole
-        ring behind.  Device and pinned memory are 2 x chunkBytes each whatever the run length
+        the writer threads).  The pinned ring is PIN_SLOTS (two; MCMCN_STORE_PIN_SLOTS) chunks deep: the thread
+        that launches the kernels runs PIN_SLOTS - 1 chunks ahead of the writers and then waits for a slot -- its
+        run-ahead being throttled, the device has the next chunk's launches queued meanwhile.  Device memory is
+        2 x chunkBytes and pinned memory PIN_SLOTS x chunkBytes whatever the run length
         (posteriorSampling.py:898-909, :933-936 appends a CSV row per retained iteration; this is the
         same stream of rows in binary).  ``Engine.run`` splits its iterations at chunk boundaries;
         ``finish()`` drains the ring.
@@ -184,6 +190,7 @@ class SampleStore(object):
             (self.logLik.numel() * 8 if self.logLik is not None else 0)
         if self.streamed:
             self._chunk, self._fill, self._done = 0, 0, 0          # ring position; rows already handed to the sink
+            self.pinSlots = max(2, min(PIN_SLOTS, -(-self.nRows // self.chunkRows)))
             self._side = torch.cuda.Stream(dev)
             # The pinned staging buffers (2 x chunkBytes: 0.6 s of cudaHostAlloc at 1 GB) are allocated by a background
             # thread: the first chunk is full only after the burn-in, so the chains start without waiting for them.
@@ -191,14 +198,16 @@ class SampleStore(object):
 
             def allocatePinned():
                 torch.cuda.set_device(dev)                          # the thread's own current device (default: 0)
-                pin = [torch.empty((self.chunkRows, engine.nCol, S), dtype=dtype, pin_memory=True) for _ in range(2)]
+                pin = [torch.empty((self.chunkRows, engine.nCol, S), dtype=dtype, pin_memory=True)
+                       for _ in range(self.pinSlots)]
                 pinLL = [torch.empty((self.chunkRows, engine.nObservations, S), dtype=torch.float64, pin_memory=True)
-                         for _ in range(2)] if logLikelihood else None
+                         for _ in range(self.pinSlots)] if logLikelihood else None
                 self._pin, self._pinLL = pin, pinLL
             self._pinThread = threading.Thread(target=allocatePinned, daemon=True)
             self._pinThread.start()
-            self._copied = [None, None]
-            self._written = [None, None]                            # future of the retire job that reads pinned slot c
+            self._copied = [None, None]                             # per device chunk: event of its copy to the host
+            self._written = [None] * self.pinSlots                  # per pinned slot: future of the retire job that reads it
+            self._flushes = 0
             import concurrent.futures
             self._writers = concurrent.futures.ThreadPoolExecutor(max_workers=WRITER_THREADS)
             self._retirer = concurrent.futures.ThreadPoolExecutor(max_workers=1)     # one thread: chunks retire in order
@@ -276,9 +285,11 @@ class SampleStore(object):
             self._pinThread = None
             if self._pin is None:
                 raise RuntimeError("could not allocate the pinned staging buffers of the sample store")
-        if self._written[c] is not None:            # pinned slot c still being written to the file: a whole ring behind
+        slot = self._flushes % self.pinSlots
+        self._flushes += 1
+        if self._written[slot] is not None:         # this pinned slot is still being written to the file: a whole ring behind
             t0 = time.perf_counter()
-            self._written[c].result()               # (re-raises what the retire thread raised)
+            self._written[slot].result()            # (re-raises what the retire thread raised)
             self.waitedForWriters += time.perf_counter() - t0
         main = torch.cuda.current_stream(self.engine.device)
         filled = torch.cuda.Event()
@@ -286,13 +297,13 @@ class SampleStore(object):
         self._side.wait_event(filled)
         r0 = c * self.chunkRows
         with torch.cuda.stream(self._side):
-            self._pin[c][:n].copy_(self.tensor[r0:r0 + n], non_blocking=True)
+            self._pin[slot][:n].copy_(self.tensor[r0:r0 + n], non_blocking=True)
             if self.logLik is not None:
-                self._pinLL[c][:n].copy_(self.logLik[r0:r0 + n], non_blocking=True)
+                self._pinLL[slot][:n].copy_(self.logLik[r0:r0 + n], non_blocking=True)
             done = torch.cuda.Event()
             done.record(self._side)
         self._copied[c] = done
-        self._written[c] = self._retirer.submit(self._retire, (c, n, self._done, done))
+        self._written[slot] = self._retirer.submit(self._retire, (slot, n, self._done, done))
         self._done += n
         self._chunk, self._fill = 1 - c, 0
         if self._copied[self._chunk] is not None:    # the chains may overwrite the other chunk once it has left the device
@@ -333,7 +344,7 @@ class SampleStore(object):
             if self._pinThread is not None:                    # nothing was ever flushed
                 self._pinThread.join()
                 self._pinThread = None
-            for fut in self._written:                          # the last two chunks; re-raises a writer's failure
+            for fut in self._written:                          # the last chunks; re-raises a writer's failure
                 if fut is not None:
                     fut.result()
             self._retirer.shutdown()

@@ -209,6 +209,7 @@ def _sampleShard(rank, world, nChains, nIter, burn, thin, parameterName, nGroups
     global lastRun
     lastRun = {"engine": eng, "store": store, "retained": retained, "chains": (lo, hi),
                "sampling_seconds": elapsed.total_seconds(), "store_device_bytes": store.deviceBytes,
+               "store_pinned_bytes": (store.deviceBytes // 2) * store.pinSlots if store.streamed else 0,
                "phases": phases}
     _barrier(world)                                                 # every shard file is complete
     if not useCsv and rank == 0:
