@@ -298,7 +298,7 @@ static int run_complete_split(const mcmcn_model* m, const mcmcn_state* s, const 
         }
         if (r->store && i >= r->burn && (i % r->thin) == 0) {
             if (row >= r->store_rows) { set_error("sample store overflow at row %lld", (long long)row); return MCMCN_ERR_INVALID; }
-            const dim3 sg((unsigned)P, (unsigned)((s->n_chains + 127) / 128), 1);
+            const dim3 sg((unsigned)((P + MCMCN_SNAP_COLS - 1) / MCMCN_SNAP_COLS), (unsigned)((s->n_chains + 127) / 128), 1);
             if (r->timing) r->timing[5] += 1.0;
             if (r->store_dtype == 64)
                 snapshot_kernel<double><<<sg, 128, 0, stream>>>(P, 1, 0, s->n_chains, S, s->theta, s->hyper, (double*)r->store + (size_t)row * P * S);
@@ -450,7 +450,7 @@ int mcmcn_run(const mcmcn_model* m, const mcmcn_state* s, const mcmcn_run_args* 
 
         if (r->store && i >= r->burn && (i % r->thin) == 0) {
             if (row >= r->store_rows) { set_error("sample store overflow at row %lld", (long long)row); return MCMCN_ERR_INVALID; }
-            const dim3 sg((unsigned)ncol, (unsigned)((s->n_chains + 127) / 128), 1);
+            const dim3 sg((unsigned)((ncol + MCMCN_SNAP_COLS - 1) / MCMCN_SNAP_COLS), (unsigned)((s->n_chains + 127) / 128), 1);
             tic(2);
             if (r->store_dtype == 64)
                 snapshot_kernel<double><<<sg, 128, 0, stream>>>(m->n_params, m->n_groups, partial ? 1 : 0, s->n_chains, s->stride,
