@@ -11,7 +11,6 @@ Reference symbols this module stands in for (``/root/reference/posteriorSampling
 
 import ctypes
 import os
-import math
 import threading
 import time
 
