@@ -24,6 +24,7 @@ COLOURS = {"blue": (31, 60, 230), "red": (220, 30, 30), "green": (20, 140, 40), 
            "cyan": (20, 180, 190), "yellow": (200, 180, 20), "black": (0, 0, 0)}
 CHAIN_COLOURS = ["blue", "red", "green", "magenta", "cyan", "yellow", "black"]      # :519-520
 DPI = 100                                                                            # matplotlib's default: figsize inches -> pixels
+MAX_CHAINS = int(os.environ.get("MCMCN_FIGURE_MAX_CHAINS", "56"))                    # chains drawn per figure (8 per colour)
 
 # 5 x 7 typeface, ASCII 32..126: five column bytes per glyph, bit 0 = top row (bit 7: descenders)
 _GLYPHS = bytes.fromhex(
@@ -246,14 +247,21 @@ class Axes(object):
         self.c.points(self.X(x), self.Y(y), colour, alpha, size, self.box)
 
     def bars(self, edges, heights, colour, alpha=0.5):
-        """Filled step histogram (histtype="stepfilled")."""
-        _, y0, _, y1 = self.box
-        xs = numpy.rint(self.X(edges)).astype(int)
-        tops = numpy.rint(self.Y(heights)).astype(int)
-        base = int(round(float(self.Y(0.0))))
-        for i, top in enumerate(tops):
-            self.c.fillRect(max(xs[i], self.box[0]), max(min(top, base), y0), min(max(xs[i + 1], xs[i] + 1), self.box[2] + 1),
-                            min(base, y1) + 1, colour, alpha)
+        """Filled step histogram (histtype="stepfilled"): per pixel column of the box the height of the bin it falls
+        in, one blend for the whole histogram (a bin narrower than a pixel still shows: the tallest bin of a column wins)."""
+        bx0, by0, bx1, by1 = self.box
+        xs = numpy.rint(self.X(edges)).astype(numpy.int64)
+        tops = numpy.clip(numpy.rint(self.Y(heights)).astype(numpy.int64), by0, by1)
+        base = min(int(round(float(self.Y(0.0)))), by1)
+        top = numpy.full(bx1 - bx0 + 1, base + 1, dtype=numpy.int64)          # per column: first filled row (none: below the base)
+        lo = numpy.clip(xs[:-1], bx0, bx1 + 1) - bx0
+        hi = numpy.clip(numpy.maximum(xs[1:], xs[:-1] + 1), bx0, bx1 + 1) - bx0
+        for i in numpy.nonzero(hi > lo)[0]:
+            numpy.minimum(top[lo[i]:hi[i]], min(tops[i], base), out=top[lo[i]:hi[i]])
+        rows = numpy.arange(by0, base + 1)[:, None]
+        ys, xcol = numpy.nonzero(rows >= top[None, :])
+        if ys.size:
+            self.c._blend(ys + by0, xcol + bx0, colour, alpha)
 
 
 def _colour(i):
@@ -268,7 +276,12 @@ class Figure(object):
         import sampleDiagnosis
         self._src = source if source is not None else sampleDiagnosis.openSamples(sampleDirectory)
         self._keys = list(self._src.keys)
-        self._m = self._src.nChains
+        # Chains drawn: all of them up to MAX_CHAINS (MCMCN_FIGURE_MAX_CHAINS), else that many evenly spaced ones -- a
+        # panel of a thousand overlaid traces shows nothing a panel of 56 does not (the reference stops at 7 chains)
+        nAll = self._src.nChains
+        self._chains = numpy.arange(nAll) if nAll <= MAX_CHAINS else \
+            numpy.unique(numpy.linspace(0, nAll - 1, MAX_CHAINS).round().astype(numpy.int64))
+        self._m = len(self._chains)
         self._n = self._src.nRows
         self._column = {k: i for i, k in enumerate(self._keys)}
         self._rhat = self._loadSummary(sampleDirectory)
@@ -290,7 +303,10 @@ class Figure(object):
             else:
                 blk = numpy.asarray(arr[:self._n][:, cols, :len(ids)])
             parts.append(numpy.asarray(blk, dtype=numpy.float64))
-        return numpy.transpose(numpy.concatenate(parts, axis=2), (1, 0, 2))
+        data = numpy.concatenate(parts, axis=2)
+        if self._m < data.shape[2]:
+            data = data[:, :, self._chains]
+        return numpy.transpose(data, (1, 0, 2))
 
     @staticmethod
     def _loadSummary(sampleDirectory):

@@ -150,3 +150,23 @@ def test_figures_read_the_binary_store(tmp_path):
     assert img.shape == (400, 1200, 3)
     for name in figures.CHAIN_COLOURS:
         assert _has(img[:, 600:], figures.COLOURS[name], 10), name
+
+
+def test_many_chains_are_thinned_to_evenly_spaced_ones(monkeypatch):
+    """More chains than MCMCN_FIGURE_MAX_CHAINS: that many evenly spaced chains are drawn, first and last included."""
+    import figures
+    import sampleDiagnosis as sd
+    rs = numpy.random.RandomState(1)
+    samples = rs.normal(size=(40, 30, 2))
+    samples[:, :, 0] += numpy.arange(40)[:, None]                                        # chain c sits at level c
+    src = sd.SampleSource.fromArray(samples, ["a[000]", "b[000]"])
+    monkeypatch.setattr(figures, "MAX_CHAINS", 5)
+    fig = figures.Figure("/nonexistent/", source=src)
+    assert fig._m == 5 and list(fig._chains) == [0, 10, 20, 29, 39]
+    d = fig._samples(["a[000]"])
+    assert d.shape == (1, 30, 5)
+    numpy.testing.assert_array_equal(d[0], samples[[0, 10, 20, 29, 39], :, 0].T)
+    cv = fig.traceplot(["a[000]", "b[000]"], None)
+    assert cv.px.shape == (400, 1200, 3)
+    monkeypatch.setattr(figures, "MAX_CHAINS", 56)
+    assert figures.Figure("/nonexistent/", source=src)._m == 40
