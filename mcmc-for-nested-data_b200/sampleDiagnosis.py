@@ -751,8 +751,6 @@ def _stdout_csv(content):
     print("\t" + "\n\t".join(line.replace(",", ", ") for line in content.split("\n")))
 
 
-def Figure(sampleDirectory, source=None):
-    """The reference's ``Figure`` (sampleDiagnosis.py:494-759): ``loglikelihood``, ``traceplots``, ``traceplot``,
-    ``bivariates``, ``bivariate`` with its file names; implemented in figures.py."""
-    import figures
-    return figures.Figure(sampleDirectory, source=source)
+# The reference's ``Figure`` class (sampleDiagnosis.py:494-759): ``loglikelihood``, ``traceplots``, ``traceplot``,
+# ``bivariates``, ``bivariate`` with its file names; implemented in figures.py (which imports this module lazily).
+from figures import Figure  # noqa: E402,F401
